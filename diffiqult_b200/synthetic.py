@@ -1,0 +1,65 @@
+"""Synthetic workloads named by BASELINE.json / SURVEY.md section 8(d).
+
+Geometries are the reference's own test molecules (tests/Test.py:29-76, bohr);
+the cluster and the perturbed-batch generators follow SURVEY.md 8(d) literally
+(seeds 20260101 / 20260102) so that every process builds bit-identical inputs.
+"""
+import numpy as np
+
+H2O = [(8, (0.0, 0.0, 0.091685801102911746)),
+       (1, (1.4229678834888837, 0.0, -0.98120954931681137)),
+       (1, (-1.4229678834888837, 0.0, -0.98120954931681137))]
+
+CH4 = [(6, (0.0, 0.0, 0.0)),
+       (1, (1.182181057825485, -1.182181057825485, 1.182181057825485)),
+       (1, (-1.182181057825485, 1.182181057825485, 1.182181057825485)),
+       (1, (1.182181057825485, 1.182181057825485, -1.182181057825485)),
+       (1, (-1.182181057825485, -1.182181057825485, -1.182181057825485))]
+
+H2 = [(1, (0.0, 0.0, 0.6921792096923653)), (1, (0.0, 0.0, -0.6921792096923653))]
+
+H2_EXAMPLE = [(1, (0.0, 0.0, 0.20165898)), (1, (0.0, 0.0, -1.64601435))]
+
+HCN = [(1, (0.0, 0.0, 0.0)), (6, (0.0, 0.0, 2.0125581778365533)), (7, (0.0, 0.0, 4.1914122426680516))]
+
+CH2O = [(8, (0.0, 0.0, 1.33648844)), (6, (0.0, 0.0, -0.97135846)),
+        (1, (0.0, 1.76607674, -2.17632039)), (1, (0.0, -1.76607674, -2.17632039))]
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    a, b, c, d = q
+    return np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                     [2 * (b * c + a * d), a * a - b * b + c * c - d * d, 2 * (c * d - a * b)],
+                     [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
+
+
+def water_cluster(n_mol=32, spacing=5.67, jitter=0.05, seed=20260101):
+    """n_mol rigidly rotated, jittered copies of the H2O monomer on a 4x4x2-style grid.
+
+    SURVEY.md 8(d) config 4: 32 copies, 5.67 bohr spacing, N(0, 0.05 bohr) jitter per atom,
+    numpy default_rng(20260101).  Returns the `mol` list System_mol takes; ne = 10*n_mol.
+    """
+    rng = np.random.default_rng(seed)
+    mono = np.array([p for _, p in H2O])
+    mono = mono - mono.mean(axis=0)
+    grid = [(ix, iy, iz) for iz in range(64) for iy in range(4) for ix in range(4)][:n_mol]
+    mol = []
+    for g in grid:
+        rot = _random_rotation(rng)
+        pos = mono @ rot.T + np.array(g, dtype=float) * spacing + rng.normal(scale=jitter, size=(3, 3))
+        for (z, _), p in zip(H2O, pos):
+            mol.append((z, (float(p[0]), float(p[1]), float(p[2]))))
+    return mol
+
+
+def perturbed_methanes(n=1024, sigma=0.05, seed=20260102):
+    """n copies of CH4 with i.i.d. N(0, sigma) on all 15 coordinates."""
+    rng = np.random.default_rng(seed)
+    base = np.array([p for _, p in CH4])
+    out = []
+    for _ in range(n):
+        pos = base + rng.normal(scale=sigma, size=base.shape)
+        out.append([(z, (float(p[0]), float(p[1]), float(p[2]))) for (z, _), p in zip(CH4, pos)])
+    return out
