@@ -1,0 +1,73 @@
+"""rhfenergy: the inner drop-in boundary (reference: diffiqult/Energy.py:75-324).
+
+The 19-slot positional signature built by Tasks._energy_args (Task.py:134-144) is kept, so callers written
+for the reference (Tasks, the BFGS wrapper) work unchanged; the body is one call into the CUDA library."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+SCF_FAILED = 99999  # Energy.py:322
+
+
+def _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log):
+    return _capi.SystemArrays(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
+
+
+def fockmatrix(alpha, coef, xyz, l, charges, atoms, contr_list, D, device=0):
+    """Energy.py:29-38 F = Hcore + sum_kl D_kl [2 (ij|kl) - (ik|jl)], integrals rebuilt on the device
+    (coef normalised).  Returns (F, Hcore)."""
+    a = _capi.SystemArrays(alpha, coef, xyz, l, charges, atoms, contr_list, 0, False)
+    n = a.nbasis
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    F, H = np.zeros((n, n)), np.zeros((n, n))
+    opt = _capi.options(device=device)
+    _capi.check(_capi.lib().dq_fock(C.byref(a.struct), C.byref(opt), D.ctypes, F.ctypes, H.ctypes))
+    return F, H
+
+
+def rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
+        world_size=1, rank=0, allreduce=None):
+    """Full result of one RHF single point: dict(E, status, niter, esteps, C, eps, stats)."""
+    a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
+    n = a.nbasis
+    E, nit = C.c_double(0.0), C.c_int32(0)
+    es, Cm, eps = np.zeros(max(int(max_scf), 1)), np.zeros((n, n)), np.zeros(n)
+    opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce)
+    st = _capi.check(_capi.lib().dq_rhf(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), es.ctypes, Cm.ctypes,
+                                        eps.ctypes), allow=(0, 1))
+    return dict(E=E.value, status=st, niter=nit.value, esteps=es[:nit.value].copy(), C=Cm, eps=eps, stats=_capi.stats())
+
+
+def rhf_grad(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
+             world_size=1, rank=0, allreduce=None):
+    """Energy and its gradient w.r.t. (alpha as passed, raw coefficients, Gaussian centres) in one fused pass:
+    dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats)."""
+    a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
+    E, nit = C.c_double(0.0), C.c_int32(0)
+    ga, gc, gx = np.zeros(a.nprim), np.zeros(a.nprim), np.zeros(3 * a.nbasis)
+    opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce)
+    st = _capi.check(_capi.lib().dq_rhf_grad(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), ga.ctypes, gc.ctypes,
+                                             gx.ctypes), allow=(0, 1))
+    return dict(E=E.value, status=st, niter=nit.value, grad=[ga, gc, gx], stats=_capi.stats())
+
+
+def rhfenergy(alpha_old, coef2, xyz, l, charges, xyz_atom, natoms, nbasis, contr_list, ne, max_scf, max_d, log, eigen,
+              printguess, readguess, name, write, dtype, device=0):
+    """Energy.py:75: returns E_elec + E_nuc, or 99999 when the SCF did not converge in max_scf iterations.
+
+    eigen=False (density purification) and readguess are dead / unreachable branches of the reference's public API
+     and are rejected."""
+    if not eigen:
+        raise NotImplementedError("eigen=False (canonical purification) is unreachable through Tasks and not implemented")
+    if readguess is not None:
+        raise NotImplementedError("readguess warm start is not implemented")
+    r = rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=max_scf, log=log, device=device)
+    if printguess is not None:
+        np.save(printguess, r["C"])  # Energy.py:197-198
+    if r["status"] != 0:
+        print('E_tot: ' + str(r["E"]) + '\n')
+        print('SCF DID NOT CONVERGED')
+        return SCF_FAILED
+    return r["E"]

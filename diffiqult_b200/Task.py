@@ -1,0 +1,242 @@
+"""Tasks: the user-visible task manager (reference: diffiqult/Task.py:73-473).
+
+Same constructor, same `runtask('Energy' | 'Grad' | 'Opt', **kwargs) -> bool`, same attributes (`status`,
+`energy`, `sys.grad`, `ntask`), same `.out` tape when verbose.  Underneath, every energy is one dq_rhf call and
+every gradient ONE fused dq_rhf_grad call that returns all requested argument groups at once (the reference
+runs one full forward-mode SCF per entry of argnum: Task.py:44-51).
+
+Reference quirks, decided here:
+  kept   : 99999 sentinel / status flag; kwargs such as printcoef/name are swallowed; gradient w.r.t. ln(alpha)
+           (log=True) and w.r.t. the raw coefficients; results stored in sys.grad in argnum order.
+  fixed  : gradient() evaluated everything twice (Task.py:412-413); _optupdateparam advanced the cursor by an array
+           for argnum 1 (Task.py:308-310); _optimization returned an undefined `timer` when verbose=False
+           (Task.py:346-352); Opt with argnum=[0,1,2] crashed in wrap_function (Optimize.py:281-287).
+"""
+import time
+
+import numpy as np
+
+from . import Energy as _energy
+from .Energy import rhfenergy  # noqa: F401  (re-exported like the reference's Task module)
+
+args_dict = {0: 'Exponents', 1: 'Contraction coefficients', 2: 'Gaussian centers', 4: 'Geometry centers'}
+
+
+class _GradCache(object):
+    """One fused device call serves all argument groups evaluated at the same point."""
+
+    def __init__(self):
+        self.key, self.val = None, None
+
+    def get(self, args, device):
+        key = tuple(np.asarray(args[k], dtype=np.float64).tobytes() for k in (0, 1, 2)) + (int(args[10]), bool(args[12]))
+        if key != self.key:
+            r = _energy.rhf_grad(args[0], args[1], args[2], args[3], args[4], args[5], args[8], args[9],
+                                 max_scf=args[10], log=args[12], device=device)
+            self.key, self.val = key, r
+        return self.val
+
+
+def function_grads_algopy(function, argnum, device=0):
+    """Task.py:25-41: list of callables, one per entry of argnum, each returning dE/d(args[n]) flattened.
+    (The name is the reference's; no algopy is involved: the derivative is the fused adjoint pass.)"""
+    cache = _GradCache()
+
+    def builder(narg):
+        if narg not in (0, 1, 2):
+            raise NotImplementedError("gradients exist for argnum 0 (widths), 1 (contraction coefficients), 2 (centers)")
+
+        def grad(*args, **kwargs):
+            r = cache.get(args, device)
+            if r["status"] != 0:
+                raise FloatingPointError("SCF did not converge: no gradient (the reference fails in extract_jacobian)")
+            return np.array(r["grad"][narg])
+        return grad
+    return [builder(i) for i in argnum]
+
+
+def grad_evaluator_algopy(function, args, argnum, device=0, **kwargs):
+    """Task.py:44-51."""
+    return [g(*args, **kwargs) for g in function_grads_algopy(function, argnum, device=device)]
+
+
+class Tasks(object):
+    def __init__(self, mol, name, verbose=False, device=0):
+        self.name = name
+        self.sys = mol
+        self.verbose = verbose
+        self.status = True
+        self.device = device
+        if verbose:
+            self.tape = open(name + '.out', "w")
+            self._printheader()
+        self._select_task = {"Energy": self.energy, "Opt": self.optimization, "Grad": self.gradient}
+        self.select_method = {'BFGS': self._BFGS}
+        self.ntask = 0
+
+    # ------------------------------------------------------------------ argument list (Task.py:134-144)
+    def _energy_args(self, max_scf=100, max_d=10, log=True, printguess=None, readguess=None, name='Output.molden',
+                     write=False, eigen=True):
+        alpha = np.log(self.sys.alpha) if log else self.sys.alpha
+        return [alpha, self.sys.coef, self.sys.xyz, self.sys.l, self.sys.charges, self.sys.atom, self.sys.natoms,
+                self.sys.nbasis, self.sys.list_contr, self.sys.ne, max_scf, max_d, log, eigen, printguess, readguess,
+                name, write, float(1.0)]
+
+    # ------------------------------------------------------------------ tape (Task.py:146-220)
+    def _printheader(self):
+        t = self.tape
+        t.write(' *************************************************\n DiffiQult \n')
+        t.write(' (diffiqult_b200: B200-native hot path)\n')
+        t.write(' *************************************************\n\n')
+        t.write(" Starting at %s\n" % time.asctime(time.localtime(time.time())))
+
+    def _printtail(self):
+        self.tape.write(" Finishing at %s \n" % time.asctime(time.localtime(time.time())))
+        self.tape.write(' *************************************************\n\n')
+
+    def _printenergy(self, max_scf, rguess, tol=1e-8):
+        t = self.tape
+        t.write(' SCF Initial parameters \n Maximum number of SCF: %d\n' % max_scf)
+        t.write(' Default SCF tolerance: %f\n Initial density matrix: %s\n' % (tol, str(rguess)))
+        self.sys.printcurrentgeombasis(t)
+
+    # ------------------------------------------------------------------ Grad (Task.py:223-240, 394-413)
+    def _energy_gradss(self, argnum, max_scf=100, max_d=300, readguess=None, name='Output.molden', output=False,
+                       order='first'):
+        args = self._energy_args(max_scf=max_scf, max_d=max_d, log=True, printguess=None, readguess=readguess,
+                                 name=name, write=output)
+        if self.verbose:
+            t0 = time.process_time()
+            self.tape.write(' \n Grad single point ...\n ---Start--- \n')
+            self._printenergy(max_scf, readguess)
+        try:
+            grad = grad_evaluator_algopy(rhfenergy, args, argnum, device=self.device)
+        except FloatingPointError:
+            self.status = False
+            grad = None
+        self.sys.grad = grad
+        if self.verbose:
+            self.tape.write(' ---End--- \n')
+            if grad is not None:
+                for i, argn in enumerate(argnum):
+                    self.tape.write('  %s:\n  %s\n' % (args_dict[argn], str(grad[i])))
+            self.tape.write(' Time %3.7f :\n' % (time.process_time() - t0))
+        return grad
+
+    def gradient(self, argnum=0, max_scf=30, max_d=300, printguess=None, output=False, **kwargs):
+        name = self.name + '-' + str(self.ntask)
+        if not isinstance(argnum, (list, tuple)):
+            argnum = [argnum]
+        return self._energy_gradss(list(argnum), max_scf, max_d, printguess, name, output)
+
+    # ------------------------------------------------------------------ Energy (Task.py:242-278, 415-433)
+    def _singlepoint(self, max_scf=300, max_d=300, printcoef=False, name='Output.molden', output=False):
+        pguess = name + '.npy' if printcoef else None
+        if self.verbose:
+            self.tape.write(' \n Single point ...\n ---Start--- \n')
+            self._printenergy(max_scf, None)
+            t0 = time.process_time()
+        args = self._energy_args(max_scf=max_scf, max_d=max_d, log=True, printguess=pguess, readguess=None, name=name,
+                                 write=output)
+        ene = rhfenergy(*args, device=self.device)
+        if ene == _energy.SCF_FAILED:
+            self.status = False
+            print(' SCF did not converged :( !!\n')
+        else:
+            print(' SCF converged!!')
+            print(' Energy: %3.7f' % ene)
+        self.energy = ene  # sic: the attribute shadows the method, as in the reference (Task.py:274)
+        if self.verbose:
+            self.tape.write(' ---End--- \n Time %3.7f :\n' % (time.process_time() - t0))
+            if ene == _energy.SCF_FAILED:
+                self.tape.write(' SCF did not converged :( !!\n')
+            else:
+                self.tape.write(' SCF converged!!\n Energy: %3.7f \n' % ene)
+        return ene
+
+    def energy(self, max_scf=30, max_d=300, printguess=None, output=False, **kwargs):
+        name = self.name + '-' + str(self.ntask)
+        self._singlepoint(max_scf, max_d, printguess, name, output)
+
+    # ------------------------------------------------------------------ Opt (Task.py:281-392)
+    def _BFGS(self, ene_function, grad_fun, args, argnums, log, name, **kwargs):
+        """BFGS over the selected argument groups (host loop; every f / gradient evaluation is one device call).
+        First cut on scipy.optimize.minimize: same objective, same gradients, same gtol rule (Task.py:288-291),
+        NOT the reference's modified line search, so trajectories differ from examples/*.out."""
+        from scipy.optimize import minimize
+        shapes = [np.shape(args[i]) for i in argnums]
+        sizes = [int(np.prod(s)) for s in shapes]
+        x0 = np.concatenate([np.asarray(args[i], dtype=np.float64).ravel() for i in argnums])
+        tol = 1e-05 if (log and 0 in argnums) else 1e-07
+
+        def split(x):
+            full, c = list(args), 0
+            for i, sh, sz in zip(argnums, shapes, sizes):
+                full[i] = x[c:c + sz].reshape(sh)
+                c += sz
+            return full
+
+        def f(x):
+            return ene_function(*split(x), device=self.device)
+
+        def g(x):
+            full = split(x)
+            return np.concatenate([np.ravel(gf(*full)) for gf in grad_fun])
+        return minimize(f, x0, jac=g, method='BFGS', options={'gtol': tol, 'maxiter': kwargs.get('maxiter', 30)})
+
+    def _optupdateparam(self, argnum, x):
+        c, nprim, nb = 0, len(self.sys.alpha), self.sys.nbasis
+        for i in argnum:
+            if i == 0:
+                self.sys.alpha = np.exp(x[c:c + nprim]); c += nprim
+            elif i == 1:
+                self.sys.coef = np.array(x[c:c + nprim]); c += nprim
+            elif i == 2:
+                self.sys.xyz = np.array(x[c:c + nb * 3]).reshape(nb, 3); c += nb * 3
+            else:
+                raise NotImplementedError("Optimization is restricted to contraction coefficients, exponents and Gaussian centers")
+
+    def _optimization(self, max_scf=100, log=True, scf=True, readguess=None, argnum=[0], taskname='Output', method='BFGS',
+                      penalize=None, **otherargs):
+        t0 = time.process_time()
+        if not log and 0 in argnum:
+            raise NotImplementedError("Opt on raw (non-log) exponents: _optupdateparam assumes log=True as in the reference")
+        args = self._energy_args(max_scf=max_scf, max_d=max_scf, log=log, printguess=None, readguess=None, name=taskname,
+                                 write=False)
+        grad_fun = function_grads_algopy(rhfenergy, argnum, device=self.device)
+        res = self.select_method.get(method, self._BFGS)(rhfenergy, grad_fun, args, list(argnum), log, taskname, **otherargs)
+        timer = time.process_time() - t0
+        if self.verbose:
+            t = self.tape
+            t.write(' ---End--- \n Time %3.7f :\n Message: %s\n Current energy: %f\n' % (timer, res.message, res.fun))
+            t.write(' Current gradient % f \n Number of iterations %d \n' % (np.linalg.norm(res.jac, ord=np.inf), res.nit))
+        self.status = bool(res.status == 0 or res.status == 1)
+        self._optupdateparam(argnum, res.x)
+        if self.verbose:
+            self.sys.printcurrentgeombasis(self.tape)
+        self.opt_result = res
+        return res, timer
+
+    def optimization(self, max_scf=100, log=True, scf=True, name='Output', readguess=None, output=False, argnum=[0], **kwargs):
+        name = self.name + '-task-' + str(self.ntask)
+        kwargs = {k: v for k, v in kwargs.items() if k in ('maxiter',)}
+        self._optimization(max_scf, log, scf, readguess, argnum, taskname=name, **kwargs)
+
+    # ------------------------------------------------------------------ dispatch (Task.py:435-473)
+    def runtask(self, task, **kwargs):
+        print(' Task: %s' % task)
+        self.ntask += 1
+        if self.verbose:
+            self.tape.write(' -------------------------------------------------------- \n Task: %s \n\n' % task)
+        function = self._select_task.get(task)
+        if function is None:
+            if self.verbose:
+                self.tape.write(' This task is not implemented\n')
+            return self.status
+        function(**kwargs)
+        return self.status
+
+    def end(self):
+        if self.verbose:
+            self._printtail()
+            self.tape.close()

@@ -1,0 +1,604 @@
+// diffiqult_b200 — host driver behind the C ABI (include/diffiqult_b200.h).
+//
+// Everything numerical runs in the kernels of dq_kernels.cu; this file sorts the basis into function blocks,
+// builds the tile lists, owns device memory, sequences the launches of the SCF (Energy.py:138-195) and of its
+// exact reverse sweep (DESIGN.md "gradient"), and moves results back in the caller's (reference) ordering.
+// There is no CPU fallback: without a CUDA device every entry point returns an error.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/diffiqult_b200.h"
+#include "dq_launch.h"
+#include "dq_layout.h"
+
+namespace dq {
+
+static thread_local std::string t_err;
+static thread_local dq_stats t_stats;
+
+struct Fail { int code; };
+static void fail(int code, const char* fmt, const char* a = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a);
+  t_err = buf;
+  throw Fail{code};
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) fail(-2, "CUDA error: %s", cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+  cudaStream_t st = 0;
+  std::vector<void*> owned;
+  ~Workspace() { for (void* p : owned) cudaFree(p); }
+  template <class T> T* alloc(size_t n, bool zero = false) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc(&p, n * sizeof(T)));
+    owned.push_back(p);
+    if (zero) CU(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+    return (T*)p;
+  }
+  template <class T> T* upload(const std::vector<T>& h) {
+    T* d = alloc<T>(h.size());
+    if (!h.empty()) CU(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return d;
+  }
+};
+
+struct Timer {
+  cudaEvent_t a, b; cudaStream_t st;
+  explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  double stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
+};
+
+// the sorted / blocked system on the device plus the maps back to the caller's ordering
+struct Prepared {
+  Workspace ws;
+  SystemDev sd;
+  int N = 0, nprim = 0, ne = 0, nblocks = 0, nbp = 0, kmax = 0, kkmax = 0;
+  std::vector<int> f_orig;      // sorted function -> original function
+  std::vector<int> p_orig;      // sorted primitive -> original primitive
+  std::vector<BlockPair> bps;
+  std::vector<Tile> tiles;      // this rank's tiles, grouped by class
+  int cls_start[17];
+  long long pd_len = 0;         // doubles in the pair-record buffer
+  long long n_quartets = 0, n_prim_quartets = 0;
+  // device arrays
+  double *d_alpha = nullptr, *d_lnalpha = nullptr, *d_craw = nullptr, *d_cn = nullptr, *d_xyz = nullptr, *d_pd = nullptr;
+  int *d_foff = nullptr, *d_ftype = nullptr, *d_fblock = nullptr, *d_forig = nullptr;
+  Tile* d_tiles = nullptr;
+  double* d_store = nullptr;
+  bool log_alpha = false;
+  int world = 1, rank = 0;
+  dq_allreduce_fn allreduce = nullptr; void* ar_user = nullptr;
+};
+
+static void check_system(const dq_system* s) {
+  if (!s) fail(-1, "null system");
+  if (s->nbasis <= 0 || s->nprim <= 0) fail(-1, "empty basis (nbasis == 0: a 'shifted' System_mol never fills list_contr)");
+  int np = 0;
+  for (int i = 0; i < s->nbasis; ++i) {
+    if (s->contr[i] <= 0) fail(-1, "contr[i] must be positive");
+    if (s->ltype[i] < 0 || s->ltype[i] > 3) fail(-1, "ltype must be 0 (s) or 1..3 (p): only s and p Gaussians are supported");
+    np += s->contr[i];
+  }
+  if (np != s->nprim) fail(-1, "sum(contr) != nprim");
+}
+
+static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool need_tiles, bool normalise) {
+  check_system(s);
+  int dev = opt ? opt->device : 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
+  CU(cudaSetDevice(dev));
+  P.ws.st = opt ? (cudaStream_t)opt->stream : 0;
+  cudaStream_t st = P.ws.st;
+  P.world = (opt && opt->world_size > 1) ? opt->world_size : 1;
+  P.rank = (opt && opt->world_size > 1) ? opt->rank : 0;
+  P.allreduce = opt ? opt->allreduce : nullptr;
+  P.ar_user = opt ? opt->allreduce_user : nullptr;
+  if (P.world > 1 && !P.allreduce) fail(-1, "world_size > 1 needs an allreduce callback");
+  static thread_local int boys_dev = -1;
+  if (boys_dev != dev) { if (upload_boys_constants() != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
+
+  const int N = s->nbasis;
+  P.N = N; P.nprim = s->nprim; P.ne = s->ne; P.log_alpha = s->log_alpha != 0;
+  std::vector<int> off(N + 1, 0);
+  for (int i = 0; i < N; ++i) off[i + 1] = off[i] + s->contr[i];
+  // sort functions by (type, contraction length); stable so that equal keys keep the caller's order
+  P.f_orig.resize(N);
+  for (int i = 0; i < N; ++i) P.f_orig[i] = i;
+  std::stable_sort(P.f_orig.begin(), P.f_orig.end(), [&](int a, int b) {
+    if (s->ltype[a] != s->ltype[b]) return s->ltype[a] < s->ltype[b];
+    return s->contr[a] < s->contr[b];
+  });
+  std::vector<int> foff(N + 1, 0), ftype(N), fblock(N);
+  std::vector<double> xyz(3 * N), alpha(s->nprim), craw(s->nprim);
+  P.p_orig.resize(s->nprim);
+  P.kmax = 0;
+  for (int si = 0; si < N; ++si) {
+    const int o = P.f_orig[si];
+    ftype[si] = s->ltype[o];
+    foff[si + 1] = foff[si] + s->contr[o];
+    P.kmax = std::max(P.kmax, (int)s->contr[o]);
+    for (int c = 0; c < 3; ++c) xyz[3 * si + c] = s->xyz[3 * o + c];
+    for (int p = 0; p < s->contr[o]; ++p) {
+      P.p_orig[foff[si] + p] = off[o] + p;
+      alpha[foff[si] + p] = s->alpha[off[o] + p];
+      craw[foff[si] + p] = s->coef[off[o] + p];
+    }
+  }
+  // function blocks
+  struct Blk { int s, n, type, K; };
+  std::vector<Blk> blks;
+  for (int si = 0; si < N;) {
+    const int ty = ftype[si], K = foff[si + 1] - foff[si];
+    int n = 1;
+    while (n < kBlk && si + n < N && ftype[si + n] == ty && foff[si + n + 1] - foff[si + n] == K) ++n;
+    for (int q = 0; q < n; ++q) fblock[si + q] = (int)blks.size();
+    blks.push_back({si, n, ty, K});
+    si += n;
+  }
+  const int nb = (int)blks.size();
+  P.nblocks = nb; P.nbp = nb * (nb + 1) / 2;
+  P.bps.resize(P.nbp);
+  long long offp = 0;
+  P.kkmax = 0;
+  {
+    int x = 0;
+    for (int I = 0; I < nb; ++I)
+      for (int J = I; J < nb; ++J, ++x) {
+        BlockPair& b = P.bps[x];
+        b.sI = blks[I].s; b.nI = blks[I].n; b.sJ = blks[J].s; b.nJ = blks[J].n;
+        b.axI = blks[I].type - 1; b.axJ = blks[J].type - 1;
+        b.KI = blks[I].K; b.KJ = blks[J].K; b.KK = b.KI * b.KJ; b.bI = I; b.bJ = J; b.pad_ = 0;
+        b.off = offp; offp += (long long)b.KK * kPairFields;
+        P.kkmax = std::max(P.kkmax, b.KK);
+      }
+  }
+  P.pd_len = offp * 16;
+
+  // device copies
+  Workspace& ws = P.ws;
+  P.d_foff = ws.upload(foff); P.d_ftype = ws.upload(ftype); P.d_fblock = ws.upload(fblock); P.d_forig = ws.upload(P.f_orig);
+  P.d_xyz = ws.upload(xyz); P.d_craw = ws.upload(craw);
+  std::vector<int> Z(s->natoms > 0 ? s->natoms : 1, 0);
+  std::vector<double> Cn(s->natoms > 0 ? 3 * s->natoms : 3, 0.0);
+  for (int a = 0; a < s->natoms; ++a) { Z[a] = s->charges[a]; for (int c = 0; c < 3; ++c) Cn[3 * a + c] = s->atoms[3 * a + c]; }
+  int* dZ = ws.upload(Z); double* dC = ws.upload(Cn);
+  BlockPair* dbp = ws.upload(P.bps);
+  if (P.log_alpha) {
+    P.d_lnalpha = ws.upload(alpha);
+    P.d_alpha = ws.alloc<double>(s->nprim);
+    launch_exp(st, s->nprim, P.d_lnalpha, P.d_alpha);           // Energy.py:120-121
+  } else {
+    P.d_alpha = ws.upload(alpha);
+  }
+  if (normalise) {
+    P.d_cn = ws.alloc<double>(s->nprim);
+    launch_normalize(st, N, P.d_foff, P.d_ftype, P.d_alpha, P.d_craw, P.d_cn);   // Energy.py:132
+  } else {
+    P.d_cn = P.d_craw;
+  }
+  SystemDev& sd = P.sd;
+  sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
+  sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
+  sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
+
+  if (!need_tiles) return;
+  // tiles of this rank, grouped by angular class (pI pJ | pK pL)
+  std::vector<std::vector<Tile>> by_cls(16);
+  std::vector<long long> seen(16, 0);
+  for (int b1 = 0; b1 < P.nbp; ++b1) {
+    const BlockPair& x = P.bps[b1];
+    for (int b2 = b1; b2 < P.nbp; ++b2) {
+      const BlockPair& y = P.bps[b2];
+      const int cls = (x.axI >= 0) * 8 + (x.axJ >= 0) * 4 + (y.axI >= 0) * 2 + (y.axJ >= 0);
+      if (seen[cls]++ % P.world != P.rank) continue;
+      by_cls[cls].push_back({b1, b2});
+      const long long nq = (long long)x.nI * x.nJ * y.nI * y.nJ;
+      P.n_quartets += nq; P.n_prim_quartets += nq * x.KK * y.KK;
+    }
+  }
+  P.tiles.clear();
+  for (int c = 0; c < 16; ++c) { P.cls_start[c] = (int)P.tiles.size(); P.tiles.insert(P.tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
+  P.cls_start[16] = (int)P.tiles.size();
+  P.d_tiles = ws.upload(P.tiles);
+  P.d_pd = ws.alloc<double>(P.pd_len);
+  launch_pairs(st, sd, P.d_pd);
+  if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
+}
+
+static void compute_eri_store(Prepared& P) {
+  P.d_store = P.ws.alloc<double>((size_t)P.tiles.size() * kTile);
+  for (int c = 0; c < 16; ++c)
+    launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
+                     P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
+}
+
+// unsort an N x N matrix (rows and/or columns) into the caller's ordering
+static void unsort_matrix(const Prepared& P, const std::vector<double>& in, double* out, bool rows, bool cols) {
+  const int n = P.N;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      out[(rows ? P.f_orig[i] : i) * n + (cols ? P.f_orig[j] : j)] = in[i * n + j];
+}
+
+// G[D] = 2J - K from the stored tiles (+ allreduce of the partial J|K over ranks); F = H + G if F != null
+struct JK {
+  double *JKacc;   // [2*n*n] J accumulators then K accumulators (one buffer: one allreduce)
+};
+static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, double* F, double* G) {
+  const int n = P.N;
+  cudaStream_t st = P.ws.st;
+  CU(cudaMemsetAsync(jk.JKacc, 0, sizeof(double) * 2 * n * n, st));
+  launch_jk_tiles(st, P.d_tiles, (int)P.tiles.size(), P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
+  if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, P.ar_user);
+  launch_fock_combine(st, n, P.d_fblock, H, jk.JKacc, jk.JKacc + (size_t)n * n, F, G);
+  t_stats.fock_builds++;
+}
+
+static double nuclear_repulsion(const dq_system* s) {   // Energy.py:21-27 (O(natoms^2) scalar work on the host)
+  double e = 0.0;
+  for (int i = 0; i < s->natoms; ++i)
+    for (int j = i + 1; j < s->natoms; ++j) {
+      double r2 = 0;
+      for (int c = 0; c < 3; ++c) { const double d = s->atoms[3 * j + c] - s->atoms[3 * i + c]; r2 += d * d; }
+      e = e + s->charges[i] * s->charges[j] / sqrt(r2);
+    }
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SCF (+ optional gradient)
+// ---------------------------------------------------------------------------------------------
+struct ScfOut { double E = 0; int niter = 0; bool converged = false; std::vector<double> esteps, C, eps; };
+
+static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool want_grad, double* g_alpha, double* g_coef,
+                    double* g_xyz) {
+  memset(&t_stats, 0, sizeof t_stats);
+  reset_launch_count();
+  Prepared P;
+  const int max_scf = (opt && opt->max_scf > 0) ? opt->max_scf : 30;
+  const double tol = (opt && opt->e_tol > 0) ? opt->e_tol : 1e-8;
+  if (s->ne <= 0 || s->ne > s->nbasis) fail(-1, "ne (doubly-occupied orbitals) must be in 1..nbasis");
+  cudaStream_t st0 = opt ? (cudaStream_t)opt->stream : 0;
+  CU(cudaSetDevice(opt ? opt->device : 0));
+  Timer t_total(st0);
+  Timer t_setup(st0);
+  prepare(P, s, opt, true, true);
+  Workspace& ws = P.ws;
+  cudaStream_t st = ws.st;
+  const int n = P.N, ne = P.ne;
+  const size_t nn = (size_t)n * n;
+  t_stats.ms_setup = t_setup.stop();
+  t_stats.n_tiles = (int64_t)P.tiles.size(); t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
+
+  Timer t_1e(st);
+  double *S = ws.alloc<double>(nn), *T = ws.alloc<double>(nn), *V = ws.alloc<double>(nn), *H = ws.alloc<double>(nn);
+  launch_one_electron(st, P.sd, S, T, V);
+  launch_axpby(st, (int)nn, 1.0, T, 0.0, H);
+  launch_axpby(st, (int)nn, 1.0, V, 1.0, H);                                  // Energy.py:137
+  t_stats.ms_one_electron = t_1e.stop();
+
+  Timer t_eri(st);
+  compute_eri_store(P);                                                        // Energy.py:136
+  t_stats.ms_eri = t_eri.stop();
+
+  Timer t_scf(st);
+  // S^-1/2 = L diag(w^-1/2) L^T                                               // Energy.py:138-144
+  double *L = ws.alloc<double>(nn), *wS = ws.alloc<double>(n), *X = ws.alloc<double>(nn), *t1 = ws.alloc<double>(nn),
+         *t2 = ws.alloc<double>(nn), *t3 = ws.alloc<double>(nn), *vwork = ws.alloc<double>(nn);
+  CU(cudaMemcpyAsync(t1, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  launch_eigh(st, n, 1, t1, vwork, L, wS);
+  launch_scale_cols_rsqrt(st, n, L, wS, t2);
+  launch_gemm(st, false, true, n, n, n, t2, n, L, n, X, n, 1.0, 0.0);
+
+  JK jk; jk.JKacc = ws.alloc<double>(2 * nn);
+  double *F = ws.alloc<double>(nn), *Fp = ws.alloc<double>(nn), *U = ws.alloc<double>(nn), *C = ws.alloc<double>(nn),
+         *D = ws.alloc<double>(nn), *eps = ws.alloc<double>(n), *dE = ws.alloc<double>(1);
+  // history for the reverse sweep: F_{t-1}, U_t, eps_t, D_t, F_t
+  std::vector<double*> hFprev, hU, hEps, hD, hF;
+  CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));          // Energy.py:159 (core guess)
+  double oldE = 1e8, e_elec = 0.0;
+  out.esteps.clear();
+  out.converged = false;
+  for (int it = 0; it < max_scf; ++it) {
+    if (want_grad) { double* f = ws.alloc<double>(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st)); hFprev.push_back(f); }
+    launch_gemm(st, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
+    launch_gemm(st, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
+    launch_eigh(st, n, 1, Fp, vwork, U, eps);                                  // Energy.py:167-168
+    launch_gemm(st, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
+    launch_gemm(st, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180
+    fock_build(P, jk, D, H, F, nullptr);                                       // Energy.py:188
+    launch_dot3(st, (int)nn, D, H, F, dE);                                     // Energy.py:189
+    CU(cudaMemcpyAsync(&e_elec, dE, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out.esteps.push_back(e_elec);
+    out.niter = it + 1;
+    if (want_grad) {
+      double *u = ws.alloc<double>(nn), *e = ws.alloc<double>(n), *d = ws.alloc<double>(nn), *f = ws.alloc<double>(nn);
+      CU(cudaMemcpyAsync(u, U, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(e, eps, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(d, D, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      hU.push_back(u); hEps.push_back(e); hD.push_back(d); hF.push_back(f);
+    }
+    if (fabs(e_elec - oldE) < tol) { out.converged = true; break; }          // Energy.py:192-194
+    oldE = e_elec;
+  }
+  out.E = e_elec + nuclear_repulsion(s);                                       // Energy.py:196, 316/324
+  {
+    std::vector<double> hc(nn), he(n);
+    CU(cudaMemcpyAsync(hc.data(), C, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(he.data(), eps, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out.C.resize(nn); out.eps = he;
+    unsort_matrix(P, hc, out.C.data(), true, false);
+  }
+  t_stats.ms_scf = t_scf.stop();
+  t_stats.scf_iterations = out.niter;
+
+  if (want_grad) {
+    // ---- exact reverse sweep of the k iterations actually performed
+    Timer t_rev(st);
+    const int k = out.niter;
+    double *Dbar = ws.alloc<double>(nn), *Hbar = ws.alloc<double>(nn), *Xbar = ws.alloc<double>(nn, true), *Pm = ws.alloc<double>(nn),
+           *Fbar = ws.alloc<double>(nn), *Y = ws.alloc<double>(nn);
+    double* At = ws.alloc<double>((size_t)k * nn);
+    double* Bt = ws.alloc<double>((size_t)k * nn);
+    int nterms = 0;
+    launch_axpby(st, (int)nn, 2.0, hF[k - 1], 0.0, Dbar);
+    launch_axpby(st, (int)nn, 2.0, hD[k - 1], 0.0, Hbar);
+    CU(cudaMemcpyAsync(At, hD[k - 1], nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(Bt, hD[k - 1], nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    nterms = 1;
+    for (int t = k; t >= 1; --t) {
+      double* Ut = hU[t - 1];
+      launch_gemm(st, false, true, n, n, ne, Ut, n, Ut, n, Pm, n, 1.0, 0.0);      // P_t = U_occ U_occ^T
+      launch_gemm(st, false, false, n, n, n, Dbar, n, X, n, t1, n, 1.0, 0.0);     // t1 = Dbar X
+      launch_gemm(st, false, false, n, n, n, t1, n, Pm, n, t2, n, 1.0, 0.0);      // t2 = Dbar X P
+      launch_add_transpose(st, n, t2, Xbar);                                       // Xbar += t2 + t2^T
+      launch_gemm(st, false, false, n, n, n, X, n, t1, n, t2, n, 1.0, 0.0);       // Pbar = X Dbar X
+      launch_gemm(st, true, false, n, n, n, Ut, n, t2, n, t1, n, 1.0, 0.0);       // U^T Pbar
+      launch_gemm(st, false, false, n, n, n, t1, n, Ut, n, t2, n, 1.0, 0.0);      // Z = U^T Pbar U
+      launch_make_y(st, n, ne, t2, hEps[t - 1], Y);
+      launch_gemm(st, false, false, n, n, n, Ut, n, Y, n, t1, n, 1.0, 0.0);       // U Y
+      launch_gemm(st, false, true, n, n, n, t1, n, Ut, n, t2, n, 1.0, 0.0);       // Abar = U Y U^T
+      launch_gemm(st, false, false, n, n, n, t2, n, X, n, t1, n, 1.0, 0.0);       // t1 = Abar X
+      launch_gemm(st, false, false, n, n, n, t1, n, hFprev[t - 1], n, t3, n, 1.0, 0.0);   // Abar X F_{t-1}
+      launch_add_transpose(st, n, t3, Xbar);
+      launch_gemm(st, false, false, n, n, n, X, n, t1, n, Fbar, n, 1.0, 0.0);     // Fbar = X Abar X
+      launch_symmetrize(st, n, Fbar);
+      launch_axpby(st, (int)nn, 1.0, Fbar, 1.0, Hbar);
+      if (t > 1) {
+        CU(cudaMemcpyAsync(At + (size_t)nterms * nn, Fbar, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(Bt + (size_t)nterms * nn, hD[t - 2], nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        ++nterms;
+        fock_build(P, jk, Fbar, nullptr, nullptr, Dbar);                           // Dbar_{t-1} = G[Fbar]
+      }
+    }
+    // Sbar = L [ (L^T Xbar L) o Phi ] L^T
+    double* Sbar = ws.alloc<double>(nn);
+    launch_gemm(st, true, false, n, n, n, L, n, Xbar, n, t1, n, 1.0, 0.0);
+    launch_gemm(st, false, false, n, n, n, t1, n, L, n, t2, n, 1.0, 0.0);
+    launch_phi_rsqrt(st, n, wS, t2);
+    launch_gemm(st, false, false, n, n, n, L, n, t2, n, t1, n, 1.0, 0.0);
+    launch_gemm(st, false, true, n, n, n, t1, n, L, n, Sbar, n, 1.0, 0.0);
+    t_stats.ms_reverse = t_rev.stop();
+
+    Timer t_g(st);
+    if (eri_grad_smem_bytes(P.kkmax) > 220 * 1024) fail(-1, "contraction too long for the ERI-gradient kernel's shared-memory accumulators");
+    const long long adj_len = P.pd_len / kPairFields * kAdjFields;
+    double* padj = ws.alloc<double>(adj_len, true);
+    double* pasum = ws.alloc<double>((size_t)P.nbp * 2 * 16, true);
+    // gbuf = [g_alpha | g_coef(normalised) | g_xyz]  (one buffer: one allreduce)
+    double* gbuf = ws.alloc<double>((size_t)2 * P.nprim + 3 * n, true);
+    double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
+    for (int c = 0; c < 16; ++c)
+      launch_eri_grad_tiles(st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd, nterms, At, Bt,
+                            padj, pasum, P.kkmax);
+    launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
+    if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);
+    launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, ga, gc, gx);
+    double* graw = ws.alloc<double>(P.nprim);
+    launch_normalize_bwd(st, n, P.d_foff, P.d_ftype, P.d_alpha, P.d_craw, gc, ga, graw);
+    if (P.log_alpha) launch_mul(st, P.nprim, ga, P.d_alpha, ga);                   // d/d ln(alpha) = alpha d/d alpha
+    std::vector<double> ha(P.nprim), hc(P.nprim), hx(3 * n);
+    CU(cudaMemcpyAsync(ha.data(), ga, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hc.data(), graw, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hx.data(), gx, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int p = 0; p < P.nprim; ++p) { if (g_alpha) g_alpha[P.p_orig[p]] = ha[p]; if (g_coef) g_coef[P.p_orig[p]] = hc[p]; }
+    if (g_xyz) for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) g_xyz[3 * P.f_orig[i] + c] = hx[3 * i + c];
+    t_stats.ms_eri_grad = t_g.stop();
+  }
+  CU(cudaStreamSynchronize(st));
+  t_stats.ms_total = t_total.stop();
+  t_stats.launches = launch_count();
+}
+
+}  // namespace dq
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace dq;
+
+#define DQ_TRY try {
+#define DQ_CATCH } catch (const Fail& f) { return f.code; } catch (const std::exception& e) { t_err = e.what(); return -9; } return 0;
+
+extern "C" {
+
+const char* dq_last_error(void) { return t_err.c_str(); }
+void dq_get_stats(dq_stats* out) { if (out) *out = t_stats; }
+int dq_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int dq_normalization(const dq_system* sys, const dq_options* opt, double* out) {
+  DQ_TRY
+  memset(&t_stats, 0, sizeof t_stats); reset_launch_count();
+  Prepared P;
+  prepare(P, sys, opt, false, true);
+  std::vector<double> h(P.nprim);
+  CU(cudaMemcpyAsync(h.data(), P.d_cn, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, P.ws.st));
+  CU(cudaStreamSynchronize(P.ws.st));
+  for (int p = 0; p < P.nprim; ++p) out[P.p_orig[p]] = h[p];
+  t_stats.launches = launch_count();
+  DQ_CATCH
+}
+
+int dq_one_electron(const dq_system* sys, const dq_options* opt, double* S, double* T, double* V) {
+  DQ_TRY
+  memset(&t_stats, 0, sizeof t_stats); reset_launch_count();
+  Prepared P;
+  prepare(P, sys, opt, false, false);
+  const size_t nn = (size_t)P.N * P.N;
+  double *dS = P.ws.alloc<double>(nn), *dT = P.ws.alloc<double>(nn), *dV = P.ws.alloc<double>(nn);
+  launch_one_electron(P.ws.st, P.sd, dS, dT, dV);
+  std::vector<double> h(nn);
+  double* outs[3] = {S, T, V}; double* devs[3] = {dS, dT, dV};
+  for (int m = 0; m < 3; ++m) {
+    CU(cudaMemcpyAsync(h.data(), devs[m], nn * sizeof(double), cudaMemcpyDeviceToHost, P.ws.st));
+    CU(cudaStreamSynchronize(P.ws.st));
+    if (outs[m]) unsort_matrix(P, h, outs[m], true, true);
+  }
+  t_stats.launches = launch_count();
+  DQ_CATCH
+}
+
+int dq_eri_packed(const dq_system* sys, const dq_options* opt, double* eri) {
+  DQ_TRY
+  memset(&t_stats, 0, sizeof t_stats); reset_launch_count();
+  Prepared P;
+  prepare(P, sys, opt, true, false);
+  Timer t(P.ws.st);
+  compute_eri_store(P);
+  t_stats.ms_eri = t.stop();
+  const long long n = P.N, m = n * (n + 1) / 2, len = m * (m + 1) / 2;
+  double* dpk = P.ws.alloc<double>(len, true);
+  launch_scatter_packed(P.ws.st, P.d_tiles, (int)P.tiles.size(), P.sd, P.d_forig, P.d_store, dpk);
+  if (P.world > 1) P.allreduce(dpk, len, P.ar_user);
+  CU(cudaMemcpyAsync(eri, dpk, len * sizeof(double), cudaMemcpyDeviceToHost, P.ws.st));
+  CU(cudaStreamSynchronize(P.ws.st));
+  t_stats.n_tiles = (int64_t)P.tiles.size(); t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
+  t_stats.launches = launch_count();
+  DQ_CATCH
+}
+
+int dq_fock(const dq_system* sys, const dq_options* opt, const double* D, double* F, double* Hcore) {
+  DQ_TRY
+  memset(&t_stats, 0, sizeof t_stats); reset_launch_count();
+  Prepared P;
+  prepare(P, sys, opt, true, false);
+  cudaStream_t st = P.ws.st;
+  const int n = P.N; const size_t nn = (size_t)n * n;
+  compute_eri_store(P);
+  double *S = P.ws.alloc<double>(nn), *T = P.ws.alloc<double>(nn), *V = P.ws.alloc<double>(nn), *H = P.ws.alloc<double>(nn);
+  launch_one_electron(st, P.sd, S, T, V);
+  launch_axpby(st, (int)nn, 1.0, T, 0.0, H);
+  launch_axpby(st, (int)nn, 1.0, V, 1.0, H);
+  std::vector<double> hd(nn);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) hd[i * n + j] = D[P.f_orig[i] * n + P.f_orig[j]];
+  double* dD = P.ws.upload(hd);
+  double* dF = P.ws.alloc<double>(nn);
+  JK jk; jk.JKacc = P.ws.alloc<double>(2 * nn);
+  fock_build(P, jk, dD, H, dF, nullptr);
+  std::vector<double> h(nn);
+  CU(cudaMemcpyAsync(h.data(), dF, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  unsort_matrix(P, h, F, true, true);
+  if (Hcore) {
+    CU(cudaMemcpyAsync(h.data(), H, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsort_matrix(P, h, Hcore, true, true);
+  }
+  t_stats.launches = launch_count();
+  DQ_CATCH
+}
+
+int dq_rhf(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* esteps, double* C, double* eps) {
+  try {
+    ScfOut o;
+    run_rhf(sys, opt, o, false, nullptr, nullptr, nullptr);
+    if (E) *E = o.E;
+    if (niter) *niter = o.niter;
+    if (esteps) for (size_t i = 0; i < o.esteps.size(); ++i) esteps[i] = o.esteps[i];
+    if (C) memcpy(C, o.C.data(), o.C.size() * sizeof(double));
+    if (eps) memcpy(eps, o.eps.data(), o.eps.size() * sizeof(double));
+    return o.converged ? 0 : 1;
+  } catch (const Fail& f) { return f.code; } catch (const std::exception& e) { t_err = e.what(); return -9; }
+}
+
+int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha, double* g_coef,
+                double* g_xyz) {
+  try {
+    ScfOut o;
+    run_rhf(sys, opt, o, true, g_alpha, g_coef, g_xyz);
+    if (E) *E = o.E;
+    if (niter) *niter = o.niter;
+    return o.converged ? 0 : 1;
+  } catch (const Fail& f) { return f.code; } catch (const std::exception& e) { t_err = e.what(); return -9; }
+}
+
+int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int32_t device) {
+  DQ_TRY
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
+  CU(cudaSetDevice(device));
+  reset_launch_count();
+  Workspace ws;
+  const size_t nn = (size_t)n * n * batch;
+  double *dA = ws.alloc<double>(nn), *dW = ws.alloc<double>(nn), *dV = ws.alloc<double>(nn), *dw = ws.alloc<double>((size_t)n * batch);
+  CU(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
+  launch_eigh(0, n, batch, dA, dW, dV, dw);
+  CU(cudaMemcpy(w, dw, (size_t)n * batch * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(V, dV, nn * sizeof(double), cudaMemcpyDeviceToHost));
+  t_stats.launches = launch_count();
+  DQ_CATCH
+}
+
+int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device) {
+  DQ_TRY
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
+  CU(cudaSetDevice(device));
+  if (upload_boys_constants() != 0) fail(-2, "constant upload failed");
+  Workspace ws;
+  double *dt = ws.alloc<double>(n), *dF_ = ws.alloc<double>((size_t)5 * n), *ddF = ws.alloc<double>((size_t)5 * n);
+  CU(cudaMemcpy(dt, t, n * sizeof(double), cudaMemcpyHostToDevice));
+  launch_boys(0, n, dt, dF_, ddF);
+  CU(cudaMemcpy(F, dF_, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(dF, ddF, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  DQ_CATCH
+}
+
+int dq_fp64_peak(int32_t device, double* tflops) {
+  DQ_TRY
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+  Workspace ws;
+  double* out = ws.alloc<double>(1);
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  launch_fp64_peak(0, blocks, 1024, out);
+  CU(cudaDeviceSynchronize());
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    Timer t(0);
+    launch_fp64_peak(0, blocks, iters, out);
+    const double ms = t.stop();
+    const double fl = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+    best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  *tflops = best;
+  DQ_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,773 @@
+// diffiqult_b200 — CUDA kernels of the RHF hot path for sm_100a (B200).  FP64 throughout.
+//
+//   k_normalize / k_normalize_bwd   contraction-coefficient normalisation + adjoint   (Integrals.py:463-501)
+//   k_pairs                         primitive-pair records                             (Integrals.py:237-249)
+//   k_one_electron(+_grad)          S, T, V and their parameter gradient                (Integrals.py:10-188)
+//   k_eri_tiles<class>              contracted ERIs, one 256-quartet tile per CTA       (Integrals.py:190-401)
+//   k_scatter_packed                tile store -> the reference's packed Eri_vec order  (Tools.py:17-51)
+//   k_jk_tiles                      J/K contraction of the stored tiles with D          (Energy.py:29-38)
+//   k_eri_grad_tiles<class>         sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode
+//   k_pair_bwd                      pair-field adjoints -> exponents, coefficients, centres
+//   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "dq_layout.h"
+#include "dq_launch.h"
+#include "dq_math.cuh"
+
+namespace dq {
+
+__constant__ BoysConst c_boys;
+static long long g_launches = 0;   // kernels launched by this library (reported by dq_stats)
+
+long long launch_count() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+
+int upload_boys_constants() {
+  BoysConst h;
+  boys_const_init(&h);
+  return (int)cudaMemcpyToSymbol(c_boys, &h, sizeof(h));
+}
+
+#define DQ_LAUNCHED() (++g_launches)
+
+// =============================================================================================
+// normalisation
+// =============================================================================================
+__global__ void k_normalize(int N, const int* __restrict__ f_off, const int* __restrict__ f_type,
+                            const double* __restrict__ alpha, const double* __restrict__ craw, double* __restrict__ cn) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= N) return;
+  const int L = f_type[f] > 0 ? 1 : 0;
+  const double pw = 0.5 * L + 0.75, e = L + 1.5;
+  const double fac = pow(2.0 / kPi, 0.75) * (L ? 2.0 : 1.0);         // (2/pi)^(3/4) * div * 2^(L/2)
+  const double div = pow(kPi, 1.5) / (L ? 2.0 : 1.0);
+  const int p0 = f_off[f], p1 = f_off[f + 1];
+  double tm = 0.0;
+  for (int p = p0; p < p1; ++p) {
+    const double up = fac * pow(alpha[p], pw) * craw[p];
+    for (int q = p0; q < p1; ++q) {
+      const double uq = fac * pow(alpha[q], pw) * craw[q];
+      tm += uq * up / pow(alpha[p] + alpha[q], e);
+    }
+  }
+  const double nrm = sqrt(tm * div);
+  for (int p = p0; p < p1; ++p) cn[p] = fac * pow(alpha[p], pw) * craw[p] / nrm;
+}
+
+// adjoint: cbar (wrt normalised coefficients) -> crawbar (=) and abar (+=)
+__global__ void k_normalize_bwd(int N, const int* __restrict__ f_off, const int* __restrict__ f_type,
+                                const double* __restrict__ alpha, const double* __restrict__ craw,
+                                const double* __restrict__ cbar, double* __restrict__ abar, double* __restrict__ crawbar) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= N) return;
+  const int L = f_type[f] > 0 ? 1 : 0;
+  const double pw = 0.5 * L + 0.75, e = L + 1.5;
+  const double fac = pow(2.0 / kPi, 0.75) * (L ? 2.0 : 1.0);
+  const double div = pow(kPi, 1.5) / (L ? 2.0 : 1.0);
+  const int p0 = f_off[f], p1 = f_off[f + 1];
+  double tm = 0.0, dot = 0.0;
+  for (int p = p0; p < p1; ++p) {
+    const double up = fac * pow(alpha[p], pw) * craw[p];
+    dot += cbar[p] * up;
+    for (int q = p0; q < p1; ++q) tm += fac * pow(alpha[q], pw) * craw[q] * up / pow(alpha[p] + alpha[q], e);
+  }
+  const double nrm = sqrt(tm * div);
+  const double nrmb = -dot / (nrm * nrm);
+  const double tmb = nrmb * div / (2.0 * nrm);
+  for (int p = p0; p < p1; ++p) {
+    const double np_ = fac * pow(alpha[p], pw);
+    const double up = np_ * craw[p];
+    double sg = 0.0, sdg = 0.0;
+    for (int q = p0; q < p1; ++q) {
+      const double uq = fac * pow(alpha[q], pw) * craw[q];
+      const double gpq = pow(alpha[p] + alpha[q], -e);
+      sg += uq * gpq;
+      sdg += uq * gpq * (-e) / (alpha[p] + alpha[q]);
+    }
+    const double ub = cbar[p] / nrm + tmb * 2.0 * sg;
+    crawbar[p] = ub * np_;
+    abar[p] += ub * up * pw / alpha[p] + tmb * 2.0 * up * sdg;
+  }
+}
+
+// =============================================================================================
+// primitive-pair records
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_pairs(SystemDev s, double* __restrict__ pd) {
+  const BlockPair b = s.bp[blockIdx.x];
+  const int lane = threadIdx.x & 15, il = lane >> 2, jl = lane & 3;
+  const bool valid = il < b.nI && jl < b.nJ;
+  const int i = b.sI + il, j = b.sJ + jl;
+  for (int pp = threadIdx.x >> 4; pp < b.KK; pp += blockDim.x >> 4) {
+    PairPrim r;
+    if (valid) {
+      const int p = s.f_off[i] + pp / b.KJ, q = s.f_off[j] + pp % b.KJ;
+      r = make_pair(s.p_alpha[p], s.p_coef[p], s.f_xyz + 3 * i, s.f_type[i], s.p_alpha[q], s.p_coef[q], s.f_xyz + 3 * j,
+                    s.f_type[j]);
+    } else {
+      r.P[0] = r.P[1] = r.P[2] = 0.0; r.g = 1.0; r.ginv = 1.0; r.K = 0.0; r.pa = r.pb = 0.0;
+    }
+    double* o = pd + ((b.off + (long long)pp * kPairFields) * 16 + lane);
+    o[0] = r.P[0]; o[16] = r.P[1]; o[32] = r.P[2]; o[48] = r.g; o[64] = r.ginv; o[80] = r.K; o[96] = r.pa; o[112] = r.pb;
+  }
+}
+
+__device__ __forceinline__ PairPrim load_pair(const double* __restrict__ rec, int lane) {
+  PairPrim r;
+  r.P[0] = rec[lane]; r.P[1] = rec[16 + lane]; r.P[2] = rec[32 + lane];
+  r.g = rec[48 + lane]; r.ginv = rec[64 + lane]; r.K = rec[80 + lane]; r.pa = rec[96 + lane]; r.pb = rec[112 + lane];
+  return r;
+}
+
+// =============================================================================================
+// one-electron integrals
+// =============================================================================================
+__device__ __forceinline__ void pair_from_linear(int x, int n, int* i, int* j) {  // inverse of i*n - i(i-1)/2 + (j-i)
+  int ii = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * x)) * 0.5);
+  while (ii > 0 && (long long)ii * n - (long long)ii * (ii - 1) / 2 > x) --ii;
+  while ((long long)(ii + 1) * n - (long long)(ii + 1) * ii / 2 <= x) ++ii;
+  *i = ii; *j = ii + (x - (ii * n - ii * (ii - 1) / 2));
+}
+
+__global__ void k_one_electron(SystemDev s, double* __restrict__ S, double* __restrict__ T, double* __restrict__ V) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = s.N;
+  if (x >= n * (n + 1) / 2) return;
+  int i, j; pair_from_linear(x, n, &i, &j);
+  double sv = 0.0, tv = 0.0, vv = 0.0;
+  for (int p = s.f_off[i]; p < s.f_off[i + 1]; ++p)
+    for (int q = s.f_off[j]; q < s.f_off[j + 1]; ++q) {
+      double a, b, c;
+      one_electron_primitive<double>(s.p_alpha[p], s.p_coef[p], s.f_xyz + 3 * i, s.f_type[i], s.p_alpha[q], s.p_coef[q],
+                                     s.f_xyz + 3 * j, s.f_type[j], s.natoms, s.Z, s.C, c_boys, &a, &b, &c);
+      sv += a; tv += b; vv += c;
+    }
+  S[i * n + j] = S[j * n + i] = sv; T[i * n + j] = T[j * n + i] = tv; V[i * n + j] = V[j * n + i] = vv;
+}
+
+// one thread per (function pair, primitive pair): contributions of Sbar:dS + Hbar:(dT+dV)
+__global__ void k_one_electron_grad(SystemDev s, int kmax, const double* __restrict__ Sbar, const double* __restrict__ Hbar,
+                                    double* __restrict__ g_alpha, double* __restrict__ g_coef, double* __restrict__ g_xyz) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = s.N;
+  const int npair = n * (n + 1) / 2;
+  const int x = (int)(id / (kmax * kmax));
+  if (x >= npair) return;
+  const int pp = (int)(id % (kmax * kmax));
+  int i, j; pair_from_linear(x, n, &i, &j);
+  const int ki = s.f_off[i + 1] - s.f_off[i], kj = s.f_off[j + 1] - s.f_off[j];
+  const int pi = pp / kmax, pj = pp % kmax;
+  if (pi >= ki || pj >= kj) return;
+  const int p = s.f_off[i] + pi, q = s.f_off[j] + pj;
+  typedef Dual<10> D;
+  D A[3], B[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { A[c] = seed<10>(s.f_xyz[3 * i + c], 4 + c); B[c] = seed<10>(s.f_xyz[3 * j + c], 7 + c); }
+  D Sv, Tv, Vv;
+  one_electron_primitive<D>(seed<10>(s.p_alpha[p], 0), seed<10>(s.p_coef[p], 2), A, s.f_type[i], seed<10>(s.p_alpha[q], 1),
+                            seed<10>(s.p_coef[q], 3), B, s.f_type[j], s.natoms, s.Z, s.C, c_boys, &Sv, &Tv, &Vv);
+  const double ws = (i == j) ? Sbar[i * n + i] : Sbar[i * n + j] + Sbar[j * n + i];
+  const double wh = (i == j) ? Hbar[i * n + i] : Hbar[i * n + j] + Hbar[j * n + i];
+  double g[10];
+#pragma unroll
+  for (int c = 0; c < 10; ++c) g[c] = ws * Sv.d[c] + wh * (Tv.d[c] + Vv.d[c]);
+  atomicAdd(g_alpha + p, g[0]); atomicAdd(g_alpha + q, g[1]);
+  atomicAdd(g_coef + p, g[2]); atomicAdd(g_coef + q, g[3]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { atomicAdd(g_xyz + 3 * i + c, g[4 + c]); atomicAdd(g_xyz + 3 * j + c, g[7 + c]); }
+}
+
+// =============================================================================================
+// ERI tiles
+// =============================================================================================
+struct TileCtx {
+  BlockPair b1, b2;
+  int il, jl, kl, ll, bl, kt;
+  bool valid;
+};
+
+__device__ __forceinline__ TileCtx tile_ctx(const Tile tl, const SystemDev& s) {
+  TileCtx c;
+  c.b1 = s.bp[tl.bp1]; c.b2 = s.bp[tl.bp2];
+  const int tid = threadIdx.x;
+  c.il = tid >> 6; c.jl = (tid >> 4) & 3; c.kl = (tid >> 2) & 3; c.ll = tid & 3;
+  c.bl = tid >> 4; c.kt = tid & 15;
+  c.valid = c.il < c.b1.nI && c.jl < c.b1.nJ && c.kl < c.b2.nI && c.ll < c.b2.nJ;
+  return c;
+}
+
+__device__ __forceinline__ void stage_pairs(const TileCtx& c, const double* __restrict__ pd, double* sbra, double* sket) {
+  const double* gb = pd + c.b1.off * 16;
+  const double* gk = pd + c.b2.off * 16;
+  const int nb = c.b1.KK * kPairFields * 16, nk = c.b2.KK * kPairFields * 16;
+  for (int x = threadIdx.x; x < nb; x += blockDim.x) sbra[x] = gb[x];
+  for (int x = threadIdx.x; x < nk; x += blockDim.x) sket[x] = gk[x];
+}
+
+template <bool LA, bool LB, bool LC, bool LD>
+__global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd,
+                                                   double* __restrict__ store) {
+  extern __shared__ double sm[];
+  const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
+  double* sbra = sm;
+  double* sket = sm + c.b1.KK * kPairFields * 16;
+  stage_pairs(c, pd, sbra, sket);
+  __syncthreads();
+  double v = 0.0;
+  if (c.valid) {
+    for (int pb = 0; pb < c.b1.KK; ++pb) {
+      const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+      for (int pk = 0; pk < c.b2.KK; ++pk) {
+        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
+        v += prim_quartet<LA, LB, LC, LD, false>(bra, ket, c.b1.axI, c.b1.axJ, c.b2.axI, c.b2.axJ, c_boys, 0.0, nullptr,
+                                                 nullptr, nullptr, nullptr, nullptr, nullptr);
+      }
+    }
+  }
+  store[(long long)blockIdx.x * kTile + threadIdx.x] = v;
+}
+
+// tile store -> reference order: Eri_vec[eri_index(i,j,k,l)] with ORIGINAL function indices (Tools.py:25-51)
+__global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__ tiles, SystemDev s, const int* __restrict__ f_orig,
+                                                        const double* __restrict__ store, double* __restrict__ packed) {
+  const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
+  if (!c.valid) return;
+  const int si = c.b1.sI + c.il, sj = c.b1.sJ + c.jl, sk = c.b2.sI + c.kl, sl = c.b2.sJ + c.ll;
+  const long long n = s.N;
+  // one canonical representative per unique quartet (diagonal tiles hold the same quartet more than once)
+  if (si > sj || sk > sl) return;
+  const long long sx = si * n - (long long)si * (si + 1) / 2 + sj, sy = sk * n - (long long)sk * (sk + 1) / 2 + sl;
+  if (sx > sy) return;
+  int i = f_orig[si], j = f_orig[sj], k = f_orig[sk], l = f_orig[sl];
+  if (i > j) { int t = i; i = j; j = t; }
+  if (k > l) { int t = k; k = l; l = t; }
+  long long x = i * n - (long long)i * (i + 1) / 2 + j, y = k * n - (long long)k * (k + 1) / 2 + l;
+  if (x > y) { long long t = x; x = y; y = t; }
+  const long long m = n * (n + 1) / 2;
+  packed[x * m - x * (x + 1) / 2 + y] = store[(long long)blockIdx.x * kTile + threadIdx.x];
+}
+
+// J/K contraction of stored tiles:  Jacc (upper block triangle) and Kacc (final K = Kacc + Kacc^T)
+__global__ void __launch_bounds__(256) k_jk_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ store,
+                                                  const double* __restrict__ D, double* __restrict__ Jacc, double* __restrict__ Kacc) {
+  __shared__ double sv[16 * 17];
+  __shared__ double sd[6][16];
+  const Tile tl = tiles[blockIdx.x];
+  const BlockPair b1 = s.bp[tl.bp1], b2 = s.bp[tl.bp2];
+  const int tid = threadIdx.x, n = s.N;
+  sv[(tid >> 4) * 17 + (tid & 15)] = store[(long long)blockIdx.x * kTile + tid];
+  const int which = tid >> 4, lane = tid & 15, r = lane >> 2, cc = lane & 3;
+  // row/column blocks of the six D (and output) sub-blocks: 0 IJ, 1 KL, 2 JL, 3 IL, 4 JK, 5 IK
+  int rs = 0, rn = 0, cs = 0, cn = 0;
+  if (which < 6) {
+    const int rsel = (which == 0 || which == 3 || which == 5) ? 0 : (which == 1 ? 2 : 1);   // 0:I 1:J 2:K
+    const int csel = (which == 0) ? 1 : ((which == 4 || which == 5) ? 2 : 3);               // 1:J 2:K 3:L
+    rs = rsel == 0 ? b1.sI : (rsel == 1 ? b1.sJ : b2.sI); rn = rsel == 0 ? b1.nI : (rsel == 1 ? b1.nJ : b2.nI);
+    cs = csel == 1 ? b1.sJ : (csel == 2 ? b2.sI : b2.sJ); cn = csel == 1 ? b1.nJ : (csel == 2 ? b2.nI : b2.nJ);
+    sd[which][lane] = (r < rn && cc < cn) ? D[(rs + r) * n + cs + cc] : 0.0;
+  }
+  __syncthreads();
+  if (which >= 6) return;
+  const double wS = tl.bp1 == tl.bp2 ? 0.5 : 1.0;
+  const bool dIJ = b1.bI == b1.bJ, dKL = b2.bI == b2.bJ;
+  double acc = 0.0, w;
+  double* out;
+  // the output sub-block of `which` pairs with the D sub-block of the complementary indices
+  if (which == 0) {        // J[i,j] += sum_kl D[k,l] v
+    w = wS * (dKL ? 1.0 : 2.0); out = Jacc;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc += sd[1][q] * sv[lane * 17 + q];
+  } else if (which == 1) { // J[k,l] += sum_ij D[i,j] v
+    w = wS * (dIJ ? 1.0 : 2.0); out = Jacc;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc += sd[0][q] * sv[q * 17 + lane];
+  } else {
+    w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0); out = Kacc;
+    if (which == 5) {        // K[i,k] += sum_jl D[j,l] v[i j k l]   (r=i, cc=k)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += sd[2][q] * sv[(r * 4 + (q >> 2)) * 17 + cc * 4 + (q & 3)];
+    } else if (which == 4) { // K[j,k] += sum_il D[i,l] v           (r=j, cc=k)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += sd[3][q] * sv[((q >> 2) * 4 + r) * 17 + cc * 4 + (q & 3)];
+    } else if (which == 3) { // K[i,l] += sum_jk D[j,k] v           (r=i, cc=l)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += sd[4][q] * sv[(r * 4 + (q >> 2)) * 17 + (q & 3) * 4 + cc];
+    } else {                 // which == 2: K[j,l] += sum_ik D[i,k] v (r=j, cc=l)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += sd[5][q] * sv[((q >> 2) * 4 + r) * 17 + (q & 3) * 4 + cc];
+    }
+  }
+  if (r < rn && cc < cn && acc != 0.0) atomicAdd(out + (rs + r) * n + cs + cc, w * acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ERI gradient: sum over the tile's quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
+//   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
+// where sum_terms <A, dG[B]> is the two-electron part of dE from the SCF reverse sweep.
+// ---------------------------------------------------------------------------------------------
+template <bool LA, bool LB, bool LC, bool LD>
+__global__ void __launch_bounds__(256, 1)
+k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd, int nterms,
+                 const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
+                 double* __restrict__ pasum) {
+  extern __shared__ double sm[];
+  const Tile tl = tiles[blockIdx.x];
+  const TileCtx c = tile_ctx(tl, s);
+  const int tid = threadIdx.x;
+  const int KKb = c.b1.KK, KKk = c.b2.KK;
+  double* sbra = sm;
+  double* sket = sbra + KKb * kPairFields * 16;
+  double* sacc = sket + KKk * kPairFields * 16;     // [(KKk*5 + 2)][256]
+  const int nslots = KKk * kAdjFields + 2;
+  stage_pairs(c, pd, sbra, sket);
+  for (int x = 0; x < nslots; ++x) sacc[x * 256 + tid] = 0.0;
+
+  double W = 0.0;
+  if (c.valid) {
+    const int n = s.N;
+    const int i = c.b1.sI + c.il, j = c.b1.sJ + c.jl, k = c.b2.sI + c.kl, l = c.b2.sJ + c.ll;
+    const size_t nn = (size_t)n * n;
+    for (int t = 0; t < nterms; ++t) {
+      const double* A = At + t * nn;
+      const double* B = Bt + t * nn;
+      W += 8.0 * (A[i * n + j] * B[k * n + l] + A[k * n + l] * B[i * n + j]) -
+           2.0 * (A[i * n + k] * B[j * n + l] + A[j * n + k] * B[i * n + l] + A[i * n + l] * B[j * n + k] +
+                  A[j * n + l] * B[i * n + k]);
+    }
+    W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (c.b1.bI == c.b1.bJ ? 0.5 : 1.0) * (c.b2.bI == c.b2.bJ ? 0.5 : 1.0);
+  }
+  __syncthreads();
+
+  const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+  const long long off5b = c.b1.off / kPairFields * kAdjFields, off5k = c.b2.off / kPairFields * kAdjFields;
+  double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
+  for (int pb = 0; pb < KKb; ++pb) {
+    const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+    PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
+    if (W != 0.0) {
+      for (int pk = 0; pk < KKk; ++pk) {
+        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
+        PairAdj ka; ka.P[0] = ka.P[1] = ka.P[2] = ka.g = ka.K = 0.0;
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+        prim_quartet<LA, LB, LC, LD, true>(bra, ket, ia, ib, ic, id, c_boys, W, &ba, &ka, &e0, &e1, &e2, &e3);
+        if (LA) { ba.P[ia] += e0; pas += e0; }
+        if (LB) { ba.P[ib] += e1; pbs += e1; }
+        if (LC) { ka.P[ic] += e2; qcs += e2; }
+        if (LD) { ka.P[id] += e3; qds += e3; }
+        double* a = sacc + (pk * kAdjFields) * 256 + tid;
+        a[0] += ka.P[0]; a[256] += ka.P[1]; a[512] += ka.P[2]; a[768] += ka.g; a[1024] += ka.K;
+      }
+    }
+    // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
+    double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
+#pragma unroll
+    for (int f = 0; f < kAdjFields; ++f) {
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) r[f] += __shfl_xor_sync(0xffffffffu, r[f], o);
+    }
+    if (c.kt == 0) {
+#pragma unroll
+      for (int f = 0; f < kAdjFields; ++f)
+        if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + c.bl, r[f]);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) { pas += __shfl_xor_sync(0xffffffffu, pas, o); pbs += __shfl_xor_sync(0xffffffffu, pbs, o); }
+  if (c.kt == 0) {
+    if (pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + c.bl, pas);
+    if (pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + c.bl, pbs);
+  }
+  sacc[(KKk * kAdjFields + 0) * 256 + tid] = qcs;
+  sacc[(KKk * kAdjFields + 1) * 256 + tid] = qds;
+  __syncthreads();
+  // ket adjoints: sum over the 16 bra lanes
+  for (int slot = tid >> 4; slot < nslots; slot += 16) {
+    double sum = 0.0;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + c.kt];
+    if (sum != 0.0) {
+      if (slot < KKk * kAdjFields) atomicAdd(padj + (off5k + slot) * 16 + c.kt, sum);
+      else atomicAdd(pasum + ((long long)tl.bp2 * 2 + (slot - KKk * kAdjFields)) * 16 + c.kt, sum);
+    }
+  }
+}
+
+// pair-field adjoints -> gradient w.r.t. exponents, NORMALISED coefficients and centres (sorted order)
+__global__ void __launch_bounds__(128) k_pair_bwd(SystemDev s, const double* __restrict__ padj, const double* __restrict__ pasum,
+                                                  double* __restrict__ g_alpha, double* __restrict__ g_coef,
+                                                  double* __restrict__ g_xyz) {
+  const int bpi = blockIdx.x;
+  const BlockPair b = s.bp[bpi];
+  const int lane = threadIdx.x & 15, il = lane >> 2, jl = lane & 3;
+  if (!(il < b.nI && jl < b.nJ)) return;
+  const int i = b.sI + il, j = b.sJ + jl;
+  const long long off5 = b.off / kPairFields * kAdjFields;
+  double Ab[3] = {0, 0, 0}, Bb[3] = {0, 0, 0};
+  const int first = threadIdx.x >> 4;
+  for (int pp = first; pp < b.KK; pp += blockDim.x >> 4) {
+    const int p = s.f_off[i] + pp / b.KJ, q = s.f_off[j] + pp % b.KJ;
+    const double* a = padj + (off5 + (long long)pp * kAdjFields) * 16 + lane;
+    PairAdj adj; adj.P[0] = a[0]; adj.P[1] = a[16]; adj.P[2] = a[32]; adj.g = a[48]; adj.K = a[64];
+    double ab = 0, bb = 0, cab = 0, cbb = 0;
+    pair_backward(s.p_alpha[p], s.p_coef[p], s.f_xyz + 3 * i, s.f_type[i], s.p_alpha[q], s.p_coef[q], s.f_xyz + 3 * j,
+                  s.f_type[j], adj, 0.0, 0.0, &ab, &bb, &cab, &cbb, Ab, Bb);
+    atomicAdd(g_alpha + p, ab); atomicAdd(g_alpha + q, bb);
+    atomicAdd(g_coef + p, cab); atomicAdd(g_coef + q, cbb);
+  }
+  if (first == 0) {   // explicit centre dependence of (P-A)_a, (P-B)_b summed over the contraction
+    if (s.f_type[i] > 0) Ab[s.f_type[i] - 1] -= pasum[((long long)bpi * 2 + 0) * 16 + lane];
+    if (s.f_type[j] > 0) Bb[s.f_type[j] - 1] -= pasum[((long long)bpi * 2 + 1) * 16 + lane];
+  }
+#pragma unroll
+  for (int x = 0; x < 3; ++x) { atomicAdd(g_xyz + 3 * i + x, Ab[x]); atomicAdd(g_xyz + 3 * j + x, Bb[x]); }
+}
+
+// =============================================================================================
+// dense helpers for the SCF and its reverse sweep
+// =============================================================================================
+// C[M,N] = alpha * op(A) op(B) + beta * C, row-major; op = transpose if TA/TB
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const double* __restrict__ A, int lda,
+                                              const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc,
+                                              double alpha, double beta) {
+  __shared__ double sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx, kb = k0 + ty;
+    sa[ty][tx] = (row < M && ka < K) ? (TA ? A[ka * lda + row] : A[row * lda + ka]) : 0.0;
+    sb[ty][tx] = (kb < K && col < N) ? (TB ? B[col * ldb + kb] : B[kb * ldb + col]) : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) C[row * ldc + col] = alpha * acc + (beta != 0.0 ? beta * C[row * ldc + col] : 0.0);
+}
+
+// symmetric eigensolver: parallel cyclic Jacobi (round-robin pairing), one CTA per matrix.
+// A (n x n, row-major, symmetric) is destroyed; eigenvalues ascending in w, eigenvectors in the columns of Vout.
+__global__ void __launch_bounds__(1024) k_eigh_jacobi(int n, double* __restrict__ Aall, double* __restrict__ Vall,
+                                                      double* __restrict__ Voutall, double* __restrict__ wall, int max_sweeps) {
+  extern __shared__ double sm[];
+  const size_t nn = (size_t)n * n;
+  double* A = Aall + blockIdx.x * nn;
+  double* V = Vall + blockIdx.x * nn;
+  double* Vout = Voutall + blockIdx.x * nn;
+  double* w = wall + (size_t)blockIdx.x * n;
+  const int m = (n + 1) / 2;        // pairs per round
+  const int np = 2 * m;             // players (one dummy if n is odd)
+  double* cs = sm;                  // [m]
+  double* sn = sm + m;              // [m]
+  int* pp = (int*)(sm + 2 * m);     // [m]
+  int* qq = pp + m;                 // [m]
+  __shared__ double red[32];
+  __shared__ double s_off, s_diag;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int x = tid; x < (int)nn; x += nt) V[x] = (x / n == x % n) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // convergence: off-diagonal Frobenius norm relative to the diagonal
+    double off = 0.0, dg = 0.0;
+    for (int x = tid; x < (int)nn; x += nt) { const double a = A[x]; if (x / n == x % n) dg += a * a; else off += a * a; }
+    for (int o = 16; o >= 1; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
+    if ((tid & 31) == 0) { red[tid >> 5] = off; }
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int x = 0; x < (nt + 31) / 32; ++x) t += red[x]; s_off = t; }
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = dg; }
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int x = 0; x < (nt + 31) / 32; ++x) t += red[x]; s_diag = t; }
+    __syncthreads();
+    if (s_off <= 1e-30 * (s_diag + s_off)) break;
+    for (int round = 0; round < np - 1; ++round) {
+      if (tid < m) {
+        int a = (tid == 0) ? np - 1 : (round + tid) % (np - 1);
+        int b = (tid == 0) ? round : (round + np - 1 - tid) % (np - 1);
+        int p = a < b ? a : b, q = a < b ? b : a;
+        double c = 1.0, s_ = 0.0;
+        if (q < n) {
+          const double apq = A[p * n + q];
+          if (fabs(apq) > 1e-300) {
+            const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = rsqrt(t * t + 1.0); s_ = t * c;
+          }
+        } else { q = -1; }
+        cs[tid] = c; sn[tid] = s_; pp[tid] = p; qq[tid] = q;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J   (row r, pair k)
+      for (int x = tid; x < m * n; x += nt) {
+        const int r = x / m, k = x % m;
+        const int q = qq[k];
+        if (q < 0 || sn[k] == 0.0) continue;
+        const int p = pp[k]; const double c = cs[k], s_ = sn[k];
+        const double arp = A[r * n + p], arq = A[r * n + q];
+        A[r * n + p] = c * arp - s_ * arq; A[r * n + q] = s_ * arp + c * arq;
+        const double vrp = V[r * n + p], vrq = V[r * n + q];
+        V[r * n + p] = c * vrp - s_ * vrq; V[r * n + q] = s_ * vrp + c * vrq;
+      }
+      __syncthreads();
+      // rows: A <- J^T A   (pair k, column cc)
+      for (int x = tid; x < m * n; x += nt) {
+        const int k = x / n, cc = x % n;
+        const int q = qq[k];
+        if (q < 0 || sn[k] == 0.0) continue;
+        const int p = pp[k]; const double c = cs[k], s_ = sn[k];
+        const double apc = A[p * n + cc], aqc = A[q * n + cc];
+        A[p * n + cc] = c * apc - s_ * aqc; A[q * n + cc] = s_ * apc + c * aqc;
+      }
+      __syncthreads();
+    }
+  }
+  // ascending order by rank
+  for (int i = tid; i < n; i += nt) {
+    const double wi = A[i * n + i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) { const double wj = A[j * n + j]; rank += (wj < wi) || (wj == wi && j < i); }
+    w[rank] = wi;
+    for (int r = 0; r < n; ++r) Vout[r * n + rank] = V[r * n + i];
+  }
+}
+
+// B[i,j] = A[i,j] * f(w[j]);  mode 0: w^-1/2
+__global__ void k_scale_cols_rsqrt(int n, const double* __restrict__ A, const double* __restrict__ w, double* __restrict__ B) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n * n) B[x] = A[x] * rsqrt(w[x % n]);
+}
+
+// F = H + 2 J - K from the tile accumulators (J: upper block triangle; K = Kacc + Kacc^T)
+__global__ void k_fock_combine(int n, const int* __restrict__ f_block, const double* __restrict__ H, const double* __restrict__ Jacc,
+                               const double* __restrict__ Kacc, double* __restrict__ F, double* __restrict__ G) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * n) return;
+  const int i = x / n, j = x % n;
+  const double jv = f_block[i] <= f_block[j] ? Jacc[i * n + j] : Jacc[j * n + i];
+  const double g = 2.0 * jv - (Kacc[i * n + j] + Kacc[j * n + i]);
+  if (G) G[x] = g;
+  if (F) F[x] = H[x] + g;
+}
+
+// out[0] = sum_x A[x] * (B[x] + C[x])   (single CTA, fixed-order tree: deterministic)
+__global__ void __launch_bounds__(1024) k_dot3(int n, const double* __restrict__ A, const double* __restrict__ B,
+                                               const double* __restrict__ C, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double acc = 0.0;
+  for (int x = threadIdx.x; x < n; x += blockDim.x) acc += A[x] * (B[x] + (C ? C[x] : 0.0));
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o >= 1; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// Y[o,v] = Y[v,o] = Z[o,v] / (eps_o - eps_v) for o < ne <= v, zero elsewhere
+__global__ void k_make_y(int n, int ne, const double* __restrict__ Z, const double* __restrict__ eps, double* __restrict__ Y) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * n) return;
+  const int i = x / n, j = x % n;
+  const bool oi = i < ne, oj = j < ne;
+  double y = 0.0;
+  if (oi != oj) { const int o = oi ? i : j, v = oi ? j : i; y = 0.5 * (Z[o * n + v] + Z[v * n + o]) / (eps[o] - eps[v]); }
+  Y[x] = y;
+}
+
+// M[i,j] *= Phi_ij,  Phi = divided difference of lambda^-1/2  (Daleckii-Krein; equal eigenvalues -> derivative)
+__global__ void k_phi_rsqrt(int n, const double* __restrict__ w, double* __restrict__ M) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * n) return;
+  const double a = w[x / n], b = w[x % n];
+  const double fa = rsqrt(a), fb = rsqrt(b);
+  // (fa - fb)/(a - b) = -1/(sqrt(a) sqrt(b) (sqrt(a)+sqrt(b))): no cancellation, valid for a == b
+  M[x] *= -fa * fb / (sqrt(a) + sqrt(b));
+}
+
+// Y = a*X + b*Y^T-or-Y ...: small elementwise family
+__global__ void k_axpby(int n, double a, const double* __restrict__ X, double b, double* __restrict__ Y) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n) Y[x] = a * X[x] + (b != 0.0 ? b * Y[x] : 0.0);
+}
+__global__ void k_symmetrize(int n, double* __restrict__ A) {   // A <- (A + A^T)/2
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * n) return;
+  const int i = x / n, j = x % n;
+  if (i < j) { const double v = 0.5 * (A[i * n + j] + A[j * n + i]); A[i * n + j] = v; A[j * n + i] = v; }
+}
+__global__ void k_add_transpose(int n, const double* __restrict__ A, double* __restrict__ B) {   // B += A + A^T
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * n) return;
+  B[x] += A[x] + A[(x % n) * n + x / n];
+}
+__global__ void k_exp(int n, const double* __restrict__ x, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = exp(x[i]);
+}
+__global__ void k_mul(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] * b[i];
+}
+
+// Boys function on its own (parity probe for Tools.py:78-151): F, dF are [n][5]
+__global__ void k_boys(int n, const double* __restrict__ t, double* __restrict__ F, double* __restrict__ dF) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double f[5], d[5];
+  boys_ref<4, true>(t[i], c_boys, f, d);
+#pragma unroll
+  for (int m = 0; m < 5; ++m) { F[5 * i + m] = f[m]; dF[5 * i + m] = d[m]; }
+}
+
+// FP64 FMA throughput probe (the FP64 roofline denominator; MEASURED_PEAKS.json has none)
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double* out) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000000001, c = 1e-12;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 123.456) out[0] = r;
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+void launch_normalize(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw, double* cn) {
+  k_normalize<<<cdiv(N, 128), 128, 0, st>>>(N, f_off, f_type, alpha, craw, cn); DQ_LAUNCHED();
+}
+void launch_normalize_bwd(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw,
+                          const double* cbar, double* abar, double* crawbar) {
+  k_normalize_bwd<<<cdiv(N, 128), 128, 0, st>>>(N, f_off, f_type, alpha, craw, cbar, abar, crawbar); DQ_LAUNCHED();
+}
+void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd) {
+  k_pairs<<<s.nbp, 128, 0, st>>>(s, pd); DQ_LAUNCHED();
+}
+void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V) {
+  k_one_electron<<<cdiv((long long)s.N * (s.N + 1) / 2, 64), 64, 0, st>>>(s, S, T, V); DQ_LAUNCHED();
+}
+void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar,
+                              double* g_alpha, double* g_coef, double* g_xyz) {
+  const long long nth = (long long)s.N * (s.N + 1) / 2 * kmax * kmax;
+  k_one_electron_grad<<<cdiv(nth, 64), 64, 0, st>>>(s, kmax, Sbar, Hbar, g_alpha, g_coef, g_xyz); DQ_LAUNCHED();
+}
+
+template <bool A, bool B, bool C, bool D>
+static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  k_eri_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
+}
+template <bool A, bool B, bool C, bool D>
+static void grad_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
+                        const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  k_eri_grad_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
+}
+
+#define DQ_CLASS_SWITCH(cls, CALL)                                                              \
+  switch (cls) {                                                                                \
+    case 0: CALL(false, false, false, false); break; case 1: CALL(false, false, false, true); break;   \
+    case 2: CALL(false, false, true, false); break;  case 3: CALL(false, false, true, true); break;    \
+    case 4: CALL(false, true, false, false); break;  case 5: CALL(false, true, false, true); break;    \
+    case 6: CALL(false, true, true, false); break;   case 7: CALL(false, true, true, true); break;     \
+    case 8: CALL(true, false, false, false); break;  case 9: CALL(true, false, false, true); break;    \
+    case 10: CALL(true, false, true, false); break;  case 11: CALL(true, false, true, true); break;    \
+    case 12: CALL(true, true, false, false); break;  case 13: CALL(true, true, false, true); break;    \
+    case 14: CALL(true, true, true, false); break;   case 15: CALL(true, true, true, true); break;     \
+  }
+
+void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
+                      int kkmax) {
+  if (nt <= 0) return;
+  const size_t smem = (size_t)2 * kkmax * kPairFields * 16 * sizeof(double);
+#define CALL(a, b, c, d) eri_launch<a, b, c, d>(st, tiles, nt, s, pd, store, smem)
+  DQ_CLASS_SWITCH(cls, CALL)
+#undef CALL
+}
+void launch_eri_grad_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
+                           const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
+  if (nt <= 0) return;
+  const size_t smem = ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kkmax * kAdjFields + 2) * 256) * sizeof(double);
+#define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, nt, s, pd, nterms, At, Bt, padj, pasum, smem)
+  DQ_CLASS_SWITCH(cls, CALL)
+#undef CALL
+}
+size_t eri_grad_smem_bytes(int kkmax) {
+  return ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kkmax * kAdjFields + 2) * 256) * sizeof(double);
+}
+void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
+                           double* packed) {
+  if (nt <= 0) return;
+  k_scatter_packed<<<nt, 256, 0, st>>>(tiles, s, f_orig, store, packed); DQ_LAUNCHED();
+}
+void launch_jk_tiles(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* store, const double* D,
+                     double* Jacc, double* Kacc) {
+  if (nt <= 0) return;
+  k_jk_tiles<<<nt, 256, 0, st>>>(tiles, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+}
+void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
+                     double* g_xyz) {
+  k_pair_bwd<<<s.nbp, 128, 0, st>>>(s, padj, pasum, g_alpha, g_coef, g_xyz); DQ_LAUNCHED();
+}
+
+void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const double* A, int lda, const double* B, int ldb,
+                 double* C, int ldc, double alpha, double beta) {
+  dim3 grid(cdiv(N, 16), cdiv(M, 16));
+  if (!ta && !tb) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+  else if (ta && !tb) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+  else if (!ta && tb) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+  DQ_LAUNCHED();
+}
+void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w) {
+  const int m = (n + 1) / 2;
+  const size_t smem = (size_t)2 * m * sizeof(double) + (size_t)2 * m * sizeof(int);
+  int threads = 1024;
+  if (n <= 16) threads = 128; else if (n <= 32) threads = 256; else if (n <= 64) threads = 512;
+  k_eigh_jacobi<<<batch, threads, smem, st>>>(n, A, Vwork, Vout, w, 60); DQ_LAUNCHED();
+}
+void launch_scale_cols_rsqrt(cudaStream_t st, int n, const double* A, const double* w, double* B) {
+  k_scale_cols_rsqrt<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, A, w, B); DQ_LAUNCHED();
+}
+void launch_fock_combine(cudaStream_t st, int n, const int* f_block, const double* H, const double* Jacc, const double* Kacc,
+                         double* F, double* G) {
+  k_fock_combine<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, f_block, H, Jacc, Kacc, F, G); DQ_LAUNCHED();
+}
+void launch_dot3(cudaStream_t st, int n, const double* A, const double* B, const double* C, double* out) {
+  k_dot3<<<1, 1024, 0, st>>>(n, A, B, C, out); DQ_LAUNCHED();
+}
+void launch_make_y(cudaStream_t st, int n, int ne, const double* Z, const double* eps, double* Y) {
+  k_make_y<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, ne, Z, eps, Y); DQ_LAUNCHED();
+}
+void launch_phi_rsqrt(cudaStream_t st, int n, const double* w, double* M) {
+  k_phi_rsqrt<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, w, M); DQ_LAUNCHED();
+}
+void launch_axpby(cudaStream_t st, int n, double a, const double* X, double b, double* Y) {
+  k_axpby<<<cdiv(n, 256), 256, 0, st>>>(n, a, X, b, Y); DQ_LAUNCHED();
+}
+void launch_symmetrize(cudaStream_t st, int n, double* A) {
+  k_symmetrize<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, A); DQ_LAUNCHED();
+}
+void launch_add_transpose(cudaStream_t st, int n, const double* A, double* B) {
+  k_add_transpose<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, A, B); DQ_LAUNCHED();
+}
+void launch_exp(cudaStream_t st, int n, const double* x, double* y) {
+  k_exp<<<cdiv(n, 256), 256, 0, st>>>(n, x, y); DQ_LAUNCHED();
+}
+void launch_mul(cudaStream_t st, int n, const double* a, const double* b, double* y) {
+  k_mul<<<cdiv(n, 256), 256, 0, st>>>(n, a, b, y); DQ_LAUNCHED();
+}
+void launch_boys(cudaStream_t st, int n, const double* t, double* F, double* dF) {
+  k_boys<<<cdiv(n, 128), 128, 0, st>>>(n, t, F, dF); DQ_LAUNCHED();
+}
+void launch_fp64_peak(cudaStream_t st, int blocks, int iters, double* out) {
+  k_fp64_peak<<<blocks, 256, 0, st>>>(iters, out); DQ_LAUNCHED();
+}
+
+}  // namespace dq

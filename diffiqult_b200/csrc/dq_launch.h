@@ -1,0 +1,48 @@
+// diffiqult_b200 — host-callable launchers of the kernels in dq_kernels.cu (all asynchronous on `st`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "dq_layout.h"
+
+namespace dq {
+
+int upload_boys_constants();
+long long launch_count();
+void reset_launch_count();
+
+void launch_normalize(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw, double* cn);
+void launch_normalize_bwd(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw,
+                          const double* cbar, double* abar, double* crawbar);
+void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd);
+void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V);
+void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar, double* g_alpha,
+                              double* g_coef, double* g_xyz);
+void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, int kkmax);
+void launch_eri_grad_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
+                           const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
+size_t eri_grad_smem_bytes(int kkmax);
+void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
+                           double* packed);
+void launch_jk_tiles(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* store, const double* D, double* Jacc,
+                     double* Kacc);
+void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
+                     double* g_xyz);
+void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+                 int ldc, double alpha, double beta);
+void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w);
+void launch_scale_cols_rsqrt(cudaStream_t st, int n, const double* A, const double* w, double* B);
+void launch_fock_combine(cudaStream_t st, int n, const int* f_block, const double* H, const double* Jacc, const double* Kacc, double* F,
+                         double* G);
+void launch_dot3(cudaStream_t st, int n, const double* A, const double* B, const double* C, double* out);
+void launch_make_y(cudaStream_t st, int n, int ne, const double* Z, const double* eps, double* Y);
+void launch_phi_rsqrt(cudaStream_t st, int n, const double* w, double* M);
+void launch_axpby(cudaStream_t st, int n, double a, const double* X, double b, double* Y);
+void launch_symmetrize(cudaStream_t st, int n, double* A);
+void launch_add_transpose(cudaStream_t st, int n, const double* A, double* B);
+void launch_exp(cudaStream_t st, int n, const double* x, double* y);
+void launch_mul(cudaStream_t st, int n, const double* a, const double* b, double* y);
+void launch_boys(cudaStream_t st, int n, const double* t, double* F, double* dF);
+void launch_fp64_peak(cudaStream_t st, int blocks, int iters, double* out);
+
+}  // namespace dq

@@ -1,0 +1,47 @@
+// diffiqult_b200 — device data layout shared by the kernels (dq_kernels.cu) and the host driver (dq_api.cu).
+//
+// Basis functions are permuted into SORTED order (key: type s/px/py/pz, contraction length) and cut into
+// FUNCTION BLOCKS of at most 4 functions of one type and one contraction length.  A TILE is a quadruple of
+// blocks (I,J | K,L) with I<=J, K<=L, pair(I,J) <= pair(K,L): 4^4 = 256 contracted quartets, one per thread
+// of a 256-thread CTA, all of one angular class, so a CTA never diverges on the integral class.
+#pragma once
+#include <stdint.h>
+
+namespace dq {
+
+constexpr int kBlk = 4;                 // functions per block
+constexpr int kTile = kBlk * kBlk * kBlk * kBlk;   // 256 quartets per tile
+constexpr int kPairLanes = kBlk * kBlk;  // 16 function pairs per block pair
+constexpr int kPairFields = 8;          // P[3], gamma, 1/gamma, Kab, (P-A)_axis(a), (P-B)_axis(b) per primitive pair
+constexpr int kAdjFields = 5;           // Pbar[3], gammabar, Kbar per primitive pair
+
+struct BlockPair {       // one per (I<=J)
+  int sI, nI, sJ, nJ;    // first sorted function and count of each block
+  int axI, axJ;          // axis (0..2) if the block is p-type, else -1
+  int KI, KJ;            // contraction lengths
+  int KK;                // KI*KJ primitive pairs
+  int bI, bJ;            // block ids
+  int pad_;
+  long long off;         // offset (in units of 16 doubles) of this block pair's primitive-pair records
+};
+
+// pair-data record layout: pd[(off + pp*kPairFields + field)*16 + lane], lane = il*4+jl
+// adjoint layout:          padj[(off5 + pp*kAdjFields + field)*16 + lane] with off5 = off/kPairFields*kAdjFields
+// contracted (pa,pb) sums: pasum[(bp*2 + which)*16 + lane]
+
+struct Tile { int bp1, bp2; };
+
+struct SystemDev {
+  int N, nprim, natoms, nblocks, nbp;
+  const int* f_off;        // [N+1] first primitive of each sorted function
+  const int* f_type;       // [N]   0 s, 1..3 p
+  const int* f_block;      // [N]   block id
+  const double* f_xyz;     // [N][3]
+  const double* p_alpha;   // [nprim] exponents
+  const double* p_coef;    // [nprim] NORMALISED contraction coefficients
+  const int* Z;            // [natoms]
+  const double* C;         // [natoms][3]
+  const BlockPair* bp;     // [nbp]
+};
+
+}  // namespace dq

@@ -1,0 +1,110 @@
+/* diffiqult_b200 — C ABI of the B200-native RHF hot path.
+ *
+ * Drop-in boundary: these entry points are what a binding of the reference's hot path
+ * would call instead of the Python functions cited beside each one.  Plain pointers and sizes only; all
+ * pointers are HOST memory unless stated, FP64, row-major, int32 indices.  Every function returns a status
+ * (0 = ok) and never exits the process (the reference's Boys failure paths call exit(): Tools.py:91,125,151).
+ * No global mutable state besides the launch counter: callable from several host threads, one per GPU.
+ *
+ * Conventions shared with the reference:
+ *   ltype[i]      0 = s, 1/2/3 = p_x/p_y/p_z   (the reference's l tuples (0,0,0),(1,0,0),(0,1,0),(0,0,1))
+ *   contr[i]      primitives of basis function i (Molecule.py:65 list_contr); primitives are stored
+ *                 function after function in alpha[] / coef[]
+ *   packed ERI    Eri_vec[eri_index(i,j,k,l)]  (Tools.py:17-51), length M(M+1)/2, M = N(N+1)/2
+ *   ne            number of doubly-occupied orbitals = electrons // 2 (Molecule.py:184)
+ */
+#ifndef DIFFIQULT_B200_H
+#define DIFFIQULT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dq_system {
+  int32_t natoms;
+  const int32_t* charges;  /* [natoms]    System_mol.charges */
+  const double* atoms;     /* [natoms*3]  System_mol.atom (bohr), kept fixed: Gaussians float */
+  int32_t nbasis;
+  const int32_t* contr;    /* [nbasis]    System_mol.list_contr */
+  const int32_t* ltype;    /* [nbasis] */
+  int32_t nprim;
+  const double* alpha;     /* [nprim]     exponents, or ln(exponent) when log_alpha != 0 (Task.py:135-136) */
+  const double* coef;      /* [nprim]     contraction coefficients (raw or normalised, see each function) */
+  const double* xyz;       /* [nbasis*3]  Gaussian centres */
+  int32_t ne;
+  int32_t log_alpha;
+} dq_system;
+
+/* in-place sum over ranks of `count` doubles at DEVICE pointer `dev`, ordered on the stream passed in
+ * dq_options.stream.  Supplied by the host language (Python: torch.distributed.all_reduce over NCCL). */
+typedef void (*dq_allreduce_fn)(void* dev, int64_t count, void* user);
+
+typedef struct dq_options {
+  int32_t max_scf;         /* Energy.py:164   (Tasks defaults: 30 'Energy'/'Grad', 100 'Opt') */
+  double e_tol;            /* Energy.py:117-118, 1e-8 when <= 0 */
+  int32_t device;          /* CUDA device ordinal */
+  void* stream;            /* cudaStream_t to run on (NULL: the default stream) */
+  int32_t world_size;      /* ERI tiles are dealt round-robin to `world_size` ranks ... */
+  int32_t rank;            /* ... this process computes the tiles of `rank` */
+  dq_allreduce_fn allreduce;   /* required when world_size > 1: sums partial J|K and gradient buffers */
+  void* allreduce_user;
+} dq_options;
+
+typedef struct dq_stats {
+  double ms_setup, ms_one_electron, ms_eri, ms_scf, ms_reverse, ms_eri_grad, ms_total;  /* CUDA-event times of the last call */
+  int64_t launches;        /* kernels launched by the last call */
+  int64_t n_tiles;         /* ERI tiles evaluated by this rank */
+  int64_t n_quartets;      /* contracted quartets (valid lanes) evaluated by this rank */
+  int64_t n_prim_quartets; /* primitive quartets evaluated by this rank (per ERI pass) */
+  int32_t scf_iterations;
+  int32_t fock_builds;     /* J/K contractions (forward + reverse sweep) */
+} dq_stats;
+
+/* Integrals.py:477-501 normalization(alpha, c, l, list_contr): sys->coef raw -> out[nprim] */
+int dq_normalization(const dq_system* sys, const dq_options* opt, double* out);
+
+/* Integrals.py:10-20, 51-62, 135-145 overlapmatrix / nuclearmatrix / kineticmatrix.
+ * sys->coef must already be normalised (as the reference's callers pass it). S,T,V: [nbasis*nbasis]. */
+int dq_one_electron(const dq_system* sys, const dq_options* opt, double* S, double* T, double* V);
+
+/* Integrals.py:190-216 erivector: sys->coef normalised; eri: packed, reference order. */
+int dq_eri_packed(const dq_system* sys, const dq_options* opt, double* eri);
+
+/* Energy.py:29-38 fockmatrix(Hcore, Eri, D): integrals are recomputed from sys (coef normalised);
+ * D: [nbasis*nbasis] symmetric; outputs F = Hcore + G[D] and (optional, may be NULL) Hcore. */
+int dq_fock(const dq_system* sys, const dq_options* opt, const double* D, double* F, double* Hcore);
+
+/* Energy.py:75-324 rhfenergy (eigen=True, readguess=None): sys->coef RAW.
+ * returns 0 converged, 1 = SCF not converged (the reference's 99999 sentinel; *E still holds the last
+ * E_elec+E_nuc), negative = error.  esteps: [max_scf] per-iteration E_elec; C: [nbasis*nbasis] AO x MO;
+ * eps: [nbasis] orbital energies.  Any of esteps, C, eps may be NULL. */
+int dq_rhf(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* esteps, double* C,
+           double* eps);
+
+/* Task.py:25-51 function_grads_algopy / grad_evaluator_algopy: gradient of the SAME truncated SCF energy,
+ * w.r.t. sys->alpha as passed (ln alpha if log_alpha), the raw coefficients, and the Gaussian centres
+ * (row-major [nbasis][3]).  One call returns all three groups; any output may be NULL. */
+int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha,
+                double* g_coef, double* g_xyz);
+
+/* Eigen.py:69-74 eigensolver on plain doubles: batch of symmetric n x n matrices -> ascending eigenvalues
+ * w[batch*n], eigenvectors in the columns of V[batch*n*n]. */
+int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int32_t device);
+
+/* Tools.py:78-83 incompletegammaf(t, m) for m = 0..4 and d/dt through the same truncated loops.
+ * F, dF: [n*5]. */
+int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device);
+
+/* measured FP64 FMA throughput of the device (TFLOP/s): the FP64 roofline denominator */
+int dq_fp64_peak(int32_t device, double* tflops);
+
+void dq_get_stats(dq_stats* out);       /* stats of the last call made by this thread */
+const char* dq_last_error(void);        /* message of the last non-zero status of this thread */
+int dq_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

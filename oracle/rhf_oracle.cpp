@@ -792,4 +792,39 @@ int orc_rhf_grad(int natoms, const int* charges, const double* atoms, int nbasis
   return rc;
 }
 
+// primitive-level probes (value + forward-mode partials) used to check the kernels' scalar math on the host
+// grad = [d/d exps (4) | d/d coefs (4) | d/d centres (12)]
+void orc_eri_primitive_grad(const double* ex, const double* co, const double* R, const int* l, double* value, double* grad) {
+  int saved = g_ndir; g_ndir = 20;
+  {
+    Fwd e[4], c[4]; V3<Fwd> r[4];
+    for (int i = 0; i < 4; ++i) {
+      e[i] = Fwd(ex[i]); e[i].d[i] = 1.0;
+      c[i] = Fwd(co[i]); c[i].d[4 + i] = 1.0;
+      for (int x = 0; x < 3; ++x) { r[i][x] = Fwd(R[3 * i + x]); r[i][x].d[8 + 3 * i + x] = 1.0; }
+    }
+    Fwd v = eris_primitive(e[0], c[0], r[0], l[0], e[1], c[1], r[1], l[1], e[2], c[2], r[2], l[2], e[3], c[3], r[3], l[3]);
+    *value = v.v;
+    for (int p = 0; p < 20; ++p) grad[p] = v.d[p];
+  }
+  g_ndir = saved;
+}
+
+// out[3][11]: S,T,V value + partials wrt (alpha, beta, ca, cb, A[3], B[3])
+void orc_one_electron_primitive_grad(double al, double ca, const double* A, int la, double be, double cb, const double* B,
+                                     int lb, int natoms, const int* Z, const double* C, double* out) {
+  int saved = g_ndir; g_ndir = 10;
+  {
+    Fwd a(al), b(be), c1(ca), c2(cb); V3<Fwd> Ad, Bd;
+    a.d[0] = 1; b.d[1] = 1; c1.d[2] = 1; c2.d[3] = 1;
+    for (int x = 0; x < 3; ++x) { Ad[x] = Fwd(A[x]); Ad[x].d[4 + x] = 1; Bd[x] = Fwd(B[x]); Bd[x].d[7 + x] = 1; }
+    Fwd r[3];
+    r[0] = overlap_primitive(a, c1, Ad, la, b, c2, Bd, lb);
+    r[1] = kinetic_primitive(a, c1, Ad, la, b, c2, Bd, lb);
+    r[2] = nuclear_primitive(a, c1, Ad, la, b, c2, Bd, lb, C, Z, natoms);
+    for (int k = 0; k < 3; ++k) { out[11 * k] = r[k].v; for (int i = 0; i < 10; ++i) out[11 * k + 1 + i] = r[k].d[i]; }
+  }
+  g_ndir = saved;
+}
+
 }  // extern "C"

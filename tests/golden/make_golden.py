@@ -154,11 +154,15 @@ def _run_energy(name, max_scf=100):
     tk = ref()["Task"].Tasks(s, os.path.join(tempfile.gettempdir(), "golden_" + name), verbose=False)
     args = tk._energy_args(max_scf=max_scf, max_d=300, log=True, name=os.path.join(tempfile.gettempdir(), "golden_" + name),
                            write=True)
-    with contextlib.redirect_stdout(io.StringIO()), ref_loader.bare_names():
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), ref_loader.bare_names():
         e = ref()["Energy"].rhfenergy(*args)
+    n = s.nbasis
+    if e == 99999:  # Energy.py:317-322: SCF did not converge within max_scf; E_tot is only printed
+        etot = [float(l.split()[1]) for l in buf.getvalue().split("\n") if l.startswith("E_tot:")][0]
+        return 99999.0, np.array([etot]), np.zeros((n, n)), np.zeros(n)
     lines = open(args[16] + ".molden").read().split("\n")
     steps = np.array([float(l.split()[2]) for l in lines if l.startswith("Step:")])
-    n = s.nbasis
     i = next(k for k, l in enumerate(lines) if l.startswith("[CM]"))
     C = np.array([[float(x) for x in l.split()[1:]] for l in lines[i + 3:i + 3 + n]])
     i = next(k for k, l in enumerate(lines) if l.startswith("[MOE]"))

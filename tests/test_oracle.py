@@ -97,6 +97,12 @@ def test_ch4_recorded_run(golden):
 def test_energy_matches_reference_source(golden, name):
     g = golden["reference_energy"]
     r = orc.rhf(arrays(name), max_scf=100)
+    if float(g[name + "_E"]) == 99999.0:
+        # plain Roothaan from the core guess does not converge for HCN within 100 iterations in the reference
+        # either (Energy.py:317-322 returns the 99999 sentinel; tests/hcn.out is a truncated run)
+        assert r["status"] == 1 and r["niter"] == 100
+        assert abs(r["E"] - float(g[name + "_steps"][0])) < 1e-6 * abs(r["E"])
+        return
     assert r["status"] == 0
     assert r["niter"] == len(g[name + "_steps"])
     assert np.abs(r["esteps"] - g[name + "_steps"]).max() < 1e-11 * max(1.0, abs(r["E"]))
