@@ -236,10 +236,13 @@ __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__
   if (!c.valid) return;
   const int si = c.b1.sI + c.il, sj = c.b1.sJ + c.jl, sk = c.b2.sI + c.kl, sl = c.b2.sJ + c.ll;
   const long long n = s.N;
-  // one canonical representative per unique quartet (diagonal tiles hold the same quartet more than once)
-  if (si > sj || sk > sl) return;
-  const long long sx = si * n - (long long)si * (si + 1) / 2 + sj, sy = sk * n - (long long)sk * (sk + 1) / 2 + sl;
-  if (sx > sy) return;
+  // one canonical representative per unique quartet: only diagonal tiles hold a quartet more than once
+  if (c.b1.bI == c.b1.bJ && si > sj) return;
+  if (c.b2.bI == c.b2.bJ && sk > sl) return;
+  if (tiles[blockIdx.x].bp1 == tiles[blockIdx.x].bp2) {
+    const int a0 = min(si, sj), a1 = max(si, sj), b0 = min(sk, sl), b1 = max(sk, sl);
+    if (a0 > b0 || (a0 == b0 && a1 > b1)) return;
+  }
   int i = f_orig[si], j = f_orig[sj], k = f_orig[sk], l = f_orig[sl];
   if (i > j) { int t = i; i = j; j = t; }
   if (k > l) { int t = k; k = l; l = t; }
