@@ -30,9 +30,9 @@ class dq_options(C.Structure):
 class dq_stats(C.Structure):
     _fields_ = [("ms_setup", C.c_double), ("ms_one_electron", C.c_double), ("ms_eri", C.c_double),
                 ("ms_scf", C.c_double), ("ms_reverse", C.c_double), ("ms_eri_grad", C.c_double),
-                ("ms_total", C.c_double), ("launches", C.c_int64), ("n_tiles", C.c_int64),
+                ("ms_grad_other", C.c_double), ("ms_total", C.c_double), ("launches", C.c_int64), ("n_tiles", C.c_int64),
                 ("n_quartets", C.c_int64), ("n_prim_quartets", C.c_int64), ("scf_iterations", C.c_int32),
-                ("fock_builds", C.c_int32)]
+                ("fock_builds", C.c_int32), ("grad_terms", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -73,6 +73,7 @@ struct Prepared {
   double *d_alpha = nullptr, *d_lnalpha = nullptr, *d_craw = nullptr, *d_cn = nullptr, *d_xyz = nullptr, *d_pd = nullptr;
   int *d_foff = nullptr, *d_ftype = nullptr, *d_fblock = nullptr, *d_forig = nullptr;
   Tile* d_tiles = nullptr;
+  int2* d_chunks = nullptr; int nchunks = 0;   // runs of tiles sharing the bra block pair (J/K contraction)
   double* d_store = nullptr;
   bool log_alpha = false;
   int world = 1, rank = 0;
@@ -210,6 +211,20 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   for (int c = 0; c < 16; ++c) { P.cls_start[c] = (int)P.tiles.size(); P.tiles.insert(P.tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
   P.cls_start[16] = (int)P.tiles.size();
   P.d_tiles = ws.upload(P.tiles);
+  {
+    constexpr int kChunk = 256;
+    std::vector<int2> chunks;
+    for (int c = 0; c < 16; ++c)
+      for (int t = P.cls_start[c]; t < P.cls_start[c + 1];) {
+        int e = t + 1;
+        while (e < P.cls_start[c + 1] && e - t < kChunk && P.tiles[e].bp1 == P.tiles[t].bp1) ++e;
+        chunks.push_back(make_int2(t, e - t));
+        t = e;
+      }
+    P.nchunks = (int)chunks.size();
+    P.d_chunks = ws.upload(chunks);
+    if (((size_t)16 * N + 2 * 16 * 17 + 16) * sizeof(double) > 220 * 1024) fail(-1, "basis too large for the J/K kernel's shared-memory row strips");
+  }
   P.d_pd = ws.alloc<double>(P.pd_len);
   launch_pairs(st, sd, P.d_pd);
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
@@ -238,7 +253,7 @@ static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, do
   const int n = P.N;
   cudaStream_t st = P.ws.st;
   CU(cudaMemsetAsync(jk.JKacc, 0, sizeof(double) * 2 * n * n, st));
-  launch_jk_tiles(st, P.d_tiles, (int)P.tiles.size(), P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
+  launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
   if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, P.ar_user);
   launch_fock_combine(st, n, P.d_fblock, H, jk.JKacc, jk.JKacc + (size_t)n * n, F, G);
   t_stats.fock_builds++;
@@ -401,9 +416,11 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     // gbuf = [g_alpha | g_coef(normalised) | g_xyz]  (one buffer: one allreduce)
     double* gbuf = ws.alloc<double>((size_t)2 * P.nprim + 3 * n, true);
     double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
+    Timer t_gk(st);
     for (int c = 0; c < 16; ++c)
       launch_eri_grad_tiles(st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd, nterms, At, Bt,
                             padj, pasum, P.kkmax);
+    t_stats.ms_eri_grad = t_gk.stop();
     launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
     if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);
     launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, ga, gc, gx);
@@ -417,7 +434,8 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     CU(cudaStreamSynchronize(st));
     for (int p = 0; p < P.nprim; ++p) { if (g_alpha) g_alpha[P.p_orig[p]] = ha[p]; if (g_coef) g_coef[P.p_orig[p]] = hc[p]; }
     if (g_xyz) for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) g_xyz[3 * P.f_orig[i] + c] = hx[3 * i + c];
-    t_stats.ms_eri_grad = t_g.stop();
+    t_stats.ms_grad_other = t_g.stop() - t_stats.ms_eri_grad;
+    t_stats.grad_terms = nterms;
   }
   CU(cudaStreamSynchronize(st));
   t_stats.ms_total = t_total.stop();

@@ -5,7 +5,7 @@
 //   k_one_electron(+_grad)          S, T, V and their parameter gradient                (Integrals.py:10-188)
 //   k_eri_tiles<class>              contracted ERIs, one 256-quartet tile per CTA       (Integrals.py:190-401)
 //   k_scatter_packed                tile store -> the reference's packed Eri_vec order  (Tools.py:17-51)
-//   k_jk_tiles                      J/K contraction of the stored tiles with D          (Energy.py:29-38)
+//   k_jk_chunks                     J/K contraction of the stored tiles with D          (Energy.py:29-38)
 //   k_eri_grad_tiles<class>         sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode
 //   k_pair_bwd                      pair-field adjoints -> exponents, coefficients, centres
 //   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
@@ -252,57 +252,88 @@ __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__
   packed[x * m - x * (x + 1) / 2 + y] = store[(long long)blockIdx.x * kTile + threadIdx.x];
 }
 
-// J/K contraction of stored tiles:  Jacc (upper block triangle) and Kacc (final K = Kacc + Kacc^T)
-__global__ void __launch_bounds__(256) k_jk_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ store,
-                                                  const double* __restrict__ D, double* __restrict__ Jacc, double* __restrict__ Kacc) {
-  __shared__ double sv[16 * 17];
-  __shared__ double sd[6][16];
-  const Tile tl = tiles[blockIdx.x];
-  const BlockPair b1 = s.bp[tl.bp1], b2 = s.bp[tl.bp2];
-  const int tid = threadIdx.x, n = s.N;
-  sv[(tid >> 4) * 17 + (tid & 15)] = store[(long long)blockIdx.x * kTile + tid];
-  const int which = tid >> 4, lane = tid & 15, r = lane >> 2, cc = lane & 3;
-  // row/column blocks of the six D (and output) sub-blocks: 0 IJ, 1 KL, 2 JL, 3 IL, 4 JK, 5 IK
-  int rs = 0, rn = 0, cs = 0, cn = 0;
-  if (which < 6) {
-    const int rsel = (which == 0 || which == 3 || which == 5) ? 0 : (which == 1 ? 2 : 1);   // 0:I 1:J 2:K
-    const int csel = (which == 0) ? 1 : ((which == 4 || which == 5) ? 2 : 3);               // 1:J 2:K 3:L
-    rs = rsel == 0 ? b1.sI : (rsel == 1 ? b1.sJ : b2.sI); rn = rsel == 0 ? b1.nI : (rsel == 1 ? b1.nJ : b2.nI);
-    cs = csel == 1 ? b1.sJ : (csel == 2 ? b2.sI : b2.sJ); cn = csel == 1 ? b1.nJ : (csel == 2 ? b2.nI : b2.nJ);
-    sd[which][lane] = (r < rn && cc < cn) ? D[(rs + r) * n + cs + cc] : 0.0;
+// J/K contraction of the stored tiles with a symmetric matrix D (Energy.py:29-38 without the N^4 index arithmetic).
+// One CTA walks a CHUNK of consecutive tiles that share the bra block pair (I,J):
+//   J[i,j]  += fKL sum_kl D_kl v      accumulated in a register per thread for the whole chunk
+//   J[k,l]  += fIJ sum_ij D_ij v      one global atomic per (tile, kl)
+//   K[i,k], K[j,k], K[i,l], K[j,l]    accumulated in two shared-memory row strips K[I,:], K[J,:], flushed once
+// with D[I,:], D[J,:] staged in shared memory.  Diagonal tiles carry weights 1/2 so that every tile is treated
+// uniformly (final J: upper block triangle mirrored; final K = Kacc + Kacc^T; DESIGN.md "Fock build").
+__global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
+                                                   const double* __restrict__ store, const double* __restrict__ D,
+                                                   double* __restrict__ Jacc, double* __restrict__ Kacc) {
+  extern __shared__ double sm[];
+  const int n = s.N, tid = threadIdx.x;
+  double* dstrip = sm;                  // [8][n]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
+  double* kstrip = sm + 8 * n;          // [8][n]
+  double* sv = kstrip + 8 * n;          // [2][16*17]
+  double* sdij = sv + 2 * 16 * 17;      // [16]
+  const int2 ch = chunks[blockIdx.x];
+  const int bp1 = tiles[ch.x].bp1;
+  const BlockPair b1 = s.bp[bp1];
+  const bool dIJ = b1.bI == b1.bJ;
+  for (int x = tid; x < 8 * n; x += 256) {
+    const int row = x / n, col = x - row * n, r = row & 3;
+    const bool isJ = row >= 4;
+    const bool ok = r < (isJ ? b1.nJ : b1.nI);
+    dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
+    kstrip[x] = 0.0;
   }
+  const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
+  if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
+  double jacc = 0.0;
   __syncthreads();
-  if (which >= 6) return;
-  const double wS = tl.bp1 == tl.bp2 ? 0.5 : 1.0;
-  const bool dIJ = b1.bI == b1.bJ, dKL = b2.bI == b2.bJ;
-  double acc = 0.0, w;
-  double* out;
-  // the output sub-block of `which` pairs with the D sub-block of the complementary indices
-  if (which == 0) {        // J[i,j] += sum_kl D[k,l] v
-    w = wS * (dKL ? 1.0 : 2.0); out = Jacc;
+  for (int t = 0; t < ch.y; ++t) {
+    const int ti = ch.x + t;
+    const int bp2 = tiles[ti].bp2;
+    const BlockPair b2 = s.bp[bp2];
+    const double v = store[(long long)ti * kTile + tid];
+    const bool dKL = b2.bI == b2.bJ;
+    const double wS = bp1 == bp2 ? 0.5 : 1.0;
+    const double dkl = (kl < b2.nI && ll < b2.nJ) ? D[(b2.sI + kl) * n + b2.sJ + ll] : 0.0;
+    jacc += (wS * (dKL ? 1.0 : 2.0)) * dkl * v;
+    double* svb = sv + (t & 1) * (16 * 17);
+    svb[bl * 17 + kt] = v;
+    __syncthreads();
+    if (tid < 16) {                      // J[k,l] (lane = kl*4+ll)
+      double acc = 0.0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc += sd[1][q] * sv[lane * 17 + q];
-  } else if (which == 1) { // J[k,l] += sum_ij D[i,j] v
-    w = wS * (dIJ ? 1.0 : 2.0); out = Jacc;
+      for (int q = 0; q < 16; ++q) acc += sdij[q] * svb[q * 17 + tid];
+      const int k = tid >> 2, l = tid & 3;
+      if (k < b2.nI && l < b2.nJ && acc != 0.0) atomicAdd(Jacc + (b2.sI + k) * n + b2.sJ + l, wS * (dIJ ? 1.0 : 2.0) * acc);
+    } else if (tid >= 32 && tid < 64) {  // K strips: thread (strip, r, x) owns K[strip row r, k = x] and K[strip row r, l = x]
+      const int u = tid - 32, strip = u >> 4, r = (u >> 2) & 3, x = u & 3;
+      const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
+      // strip 0 (rows of I): K[i,k] += sum_{j,l} D[j,l] v[i j k l];  K[i,l] += sum_{j,k} D[j,k] v
+      // strip 1 (rows of J): K[j,k] += sum_{i,l} D[i,l] v[i j k l];  K[j,l] += sum_{i,k} D[i,k] v
+      const double* dother = dstrip + (strip == 0 ? 4 : 0) * n;   // D rows of the OTHER bra block
+      double a1 = 0.0, a2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc += sd[0][q] * sv[q * 17 + lane];
-  } else {
-    w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0); out = Kacc;
-    if (which == 5) {        // K[i,k] += sum_jl D[j,l] v[i j k l]   (r=i, cc=k)
+      for (int o = 0; o < 4; ++o) {        // o: index inside the other bra block
+        const int brow = strip == 0 ? (r * 4 + o) : (o * 4 + r);   // bra lane il*4+jl
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc += sd[2][q] * sv[(r * 4 + (q >> 2)) * 17 + cc * 4 + (q & 3)];
-    } else if (which == 4) { // K[j,k] += sum_il D[i,l] v           (r=j, cc=k)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc += sd[3][q] * sv[((q >> 2) * 4 + r) * 17 + cc * 4 + (q & 3)];
-    } else if (which == 3) { // K[i,l] += sum_jk D[j,k] v           (r=i, cc=l)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc += sd[4][q] * sv[(r * 4 + (q >> 2)) * 17 + (q & 3) * 4 + cc];
-    } else {                 // which == 2: K[j,l] += sum_ik D[i,k] v (r=j, cc=l)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc += sd[5][q] * sv[((q >> 2) * 4 + r) * 17 + (q & 3) * 4 + cc];
+        for (int y = 0; y < 4; ++y) {
+          a1 += dother[o * n + b2.sJ + y] * svb[brow * 17 + x * 4 + y];   // k = x, l = y
+          a2 += dother[o * n + b2.sI + y] * svb[brow * 17 + y * 4 + x];   // k = y, l = x
+        }
+      }
+      double* ks = kstrip + (strip * 4 + r) * n;
+      if (x < b2.nI) ks[b2.sI + x] += w * a1;
+      if (x < b2.nJ) ks[b2.sJ + x] += w * a2;
     }
   }
-  if (r < rn && cc < cn && acc != 0.0) atomicAdd(out + (rs + r) * n + cs + cc, w * acc);
+  // J[i,j]: reduce the 16 ket lanes
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) jacc += __shfl_xor_sync(0xffffffffu, jacc, o);
+  if (kt == 0 && il < b1.nI && jl < b1.nJ && jacc != 0.0) atomicAdd(Jacc + (b1.sI + il) * n + b1.sJ + jl, jacc);
+  __syncthreads();
+  for (int x = tid; x < 8 * n; x += 256) {
+    const double val = kstrip[x];
+    if (val != 0.0) {
+      const int row = x / n, col = x - row * n, r = row & 3;
+      atomicAdd(Kacc + ((row >= 4 ? b1.sJ : b1.sI) + r) * n + col, val);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -709,10 +740,13 @@ void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const Sys
   if (nt <= 0) return;
   k_scatter_packed<<<nt, 256, 0, st>>>(tiles, s, f_orig, store, packed); DQ_LAUNCHED();
 }
-void launch_jk_tiles(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* store, const double* D,
-                     double* Jacc, double* Kacc) {
-  if (nt <= 0) return;
-  k_jk_tiles<<<nt, 256, 0, st>>>(tiles, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* store,
+                      const double* D, double* Jacc, double* Kacc) {
+  if (nchunks <= 0) return;
+  const size_t smem = ((size_t)16 * s.N + 2 * 16 * 17 + 16) * sizeof(double);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(k_jk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
 }
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
                      double* g_xyz) {

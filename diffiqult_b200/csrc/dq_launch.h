@@ -24,8 +24,8 @@ void launch_eri_grad_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, 
 size_t eri_grad_smem_bytes(int kkmax);
 void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
                            double* packed);
-void launch_jk_tiles(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* store, const double* D, double* Jacc,
-                     double* Kacc);
+void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* store,
+                      const double* D, double* Jacc, double* Kacc);
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
                      double* g_xyz);
 void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,

@@ -53,13 +53,16 @@ typedef struct dq_options {
 } dq_options;
 
 typedef struct dq_stats {
-  double ms_setup, ms_one_electron, ms_eri, ms_scf, ms_reverse, ms_eri_grad, ms_total;  /* CUDA-event times of the last call */
+  /* CUDA-event times of the last call: host planning + uploads, S/T/V, the ERI tile kernels, the SCF loop, its reverse
+   * sweep, the ERI-gradient tile kernels alone, the rest of the gradient assembly, and the whole call */
+  double ms_setup, ms_one_electron, ms_eri, ms_scf, ms_reverse, ms_eri_grad, ms_grad_other, ms_total;
   int64_t launches;        /* kernels launched by the last call */
   int64_t n_tiles;         /* ERI tiles evaluated by this rank */
   int64_t n_quartets;      /* contracted quartets (valid lanes) evaluated by this rank */
   int64_t n_prim_quartets; /* primitive quartets evaluated by this rank (per ERI pass) */
   int32_t scf_iterations;
   int32_t fock_builds;     /* J/K contractions (forward + reverse sweep) */
+  int32_t grad_terms;      /* rank of the two-particle weight used by the ERI-gradient pass */
 } dq_stats;
 
 /* Integrals.py:477-501 normalization(alpha, c, l, list_contr): sys->coef raw -> out[nprim] */
