@@ -310,8 +310,9 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   // S^-1/2 = L diag(w^-1/2) L^T                                               // Energy.py:138-144
   double *L = ws.alloc<double>(nn), *wS = ws.alloc<double>(n), *X = ws.alloc<double>(nn), *t1 = ws.alloc<double>(nn),
          *t2 = ws.alloc<double>(nn), *t3 = ws.alloc<double>(nn), *vwork = ws.alloc<double>(nn);
+  void* ework = ws.alloc<char>(eigh_workspace_bytes(n, 1));
   CU(cudaMemcpyAsync(t1, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  launch_eigh(st, n, 1, t1, vwork, L, wS);
+  launch_eigh(st, n, 1, t1, vwork, L, wS, ework);
   launch_scale_cols_rsqrt(st, n, L, wS, t2);
   launch_gemm(st, false, true, n, n, n, t2, n, L, n, X, n, 1.0, 0.0);
 
@@ -328,7 +329,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     if (want_grad) { double* f = ws.alloc<double>(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st)); hFprev.push_back(f); }
     launch_gemm(st, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
     launch_gemm(st, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
-    launch_eigh(st, n, 1, Fp, vwork, U, eps);                                  // Energy.py:167-168
+    launch_eigh(st, n, 1, Fp, vwork, U, eps, ework);                                  // Energy.py:167-168
     launch_gemm(st, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
     launch_gemm(st, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180
     fock_build(P, jk, D, H, F, nullptr);                                       // Energy.py:188
@@ -574,7 +575,8 @@ int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int
   const size_t nn = (size_t)n * n * batch;
   double *dA = ws.alloc<double>(nn), *dW = ws.alloc<double>(nn), *dV = ws.alloc<double>(nn), *dw = ws.alloc<double>((size_t)n * batch);
   CU(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
-  launch_eigh(0, n, batch, dA, dW, dV, dw);
+  void* ework = ws.alloc<char>(eigh_workspace_bytes(n, batch));
+  launch_eigh(0, n, batch, dA, dW, dV, dw, ework);
   CU(cudaMemcpy(w, dw, (size_t)n * batch * sizeof(double), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(V, dV, nn * sizeof(double), cudaMemcpyDeviceToHost));
   t_stats.launches = launch_count();

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "dq_layout.h"
 #include "dq_launch.h"
 #include "dq_math.cuh"
@@ -568,6 +570,148 @@ __global__ void __launch_bounds__(1024) k_eigh_jacobi(int n, double* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fast path of the symmetric eigensolver (n <= kJacobiPackedMax): two kernels.
+//  k_jacobi_packed : parallel cyclic Jacobi on A only, upper triangle PACKED in shared memory (n = 224 -> 202 KB),
+//                    one CTA per matrix.  Per round the m = n/2 disjoint rotations are applied as 2x2 block updates
+//                    B <- J_k^T B J_l for every pair of pairs (k < l): no global traffic inside the sweep.
+//                    The (c, s) of every rotation are appended to a log in global memory.
+//  k_jacobi_vectors: replays the log on the identity, one WARP per eigenvector-matrix row held in shared memory
+//                    (rows are independent, the m rotations of a round are disjoint), and writes the columns in
+//                    ascending eigenvalue order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tri_packed(int i, int j, int n) {   // i <= j
+  return i * n - ((i * (i - 1)) >> 1) + (j - i);
+}
+__device__ __forceinline__ int sym_packed(int i, int j, int n) { return i <= j ? tri_packed(i, j, n) : tri_packed(j, i, n); }
+__device__ __forceinline__ void rr_pair(int round, int k, int np, int* p, int* q) {   // round-robin tournament
+  const int a = (k == 0) ? np - 1 : (round + k) % (np - 1);
+  const int b = (k == 0) ? round : (round + np - 1 - k) % (np - 1);
+  *p = a < b ? a : b; *q = a < b ? b : a;
+}
+
+__global__ void __launch_bounds__(1024) k_jacobi_packed(int n, const double* __restrict__ Aall, unsigned short* pairtab,
+                                                        double2* __restrict__ logall, int* __restrict__ metaall,
+                                                        double* __restrict__ wall, int* __restrict__ rankall, int max_sweeps) {
+  extern __shared__ double sm[];
+  const int ne = n + (n & 1), m = ne >> 1, ntri = ne * (ne + 1) / 2;
+  const double* A = Aall + (size_t)blockIdx.x * n * n;
+  double2* log = logall + (size_t)blockIdx.x * max_sweeps * (ne - 1) * m;
+  double* Ap = sm;                 // [ntri]
+  double* cs = sm + ntri;          // [m]
+  double* sn = cs + m;             // [m]
+  int* pp = (int*)(sn + m);        // [m]
+  int* qq = pp + m;                // [m]
+  __shared__ double red[32];
+  __shared__ double s_off, s_tot;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int x = tid; x < ne * ne; x += nt) {
+    const int i = x / ne, j = x - i * ne;
+    if (i <= j) Ap[tri_packed(i, j, ne)] = (i < n && j < n) ? A[i * n + j] : 0.0;
+  }
+  const int ntask = m * (m - 1) / 2;
+  // table of the pairs of pairs (k < l), task x = l(l-1)/2 + k (every CTA writes the same values)
+  for (int x = tid; x < ntask; x += nt) {
+    int l = (int)((1.0 + sqrt(1.0 + 8.0 * x)) * 0.5);
+    while (l * (l - 1) / 2 > x) --l;
+    while ((l + 1) * l / 2 <= x) ++l;
+    pairtab[x] = (unsigned short)(((x - l * (l - 1) / 2) << 8) | l);
+  }
+  __syncthreads();
+  int rounds = 0;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // off-diagonal weight
+    double off = 0.0, tot = 0.0;
+    for (int x = tid; x < ne * ne; x += nt) {
+      const int i = x / ne, j = x - i * ne;
+      if (i <= j) { const double a = Ap[tri_packed(i, j, ne)]; if (i == j) tot += a * a; else off += 2.0 * a * a; }
+    }
+    for (int o = 16; o >= 1; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+    if ((tid & 31) == 0) red[tid >> 5] = off;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int x = 0; x < (nt + 31) / 32; ++x) t += red[x]; s_off = t; }
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = tot;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int x = 0; x < (nt + 31) / 32; ++x) t += red[x]; s_tot = t + s_off; }
+    __syncthreads();
+    if (s_off <= 1e-30 * s_tot) break;
+    for (int round = 0; round < ne - 1; ++round, ++rounds) {
+      if (tid < m) {
+        int p, q; rr_pair(round, tid, ne, &p, &q);
+        const int ipp = tri_packed(p, p, ne), iqq = tri_packed(q, q, ne), ipq = tri_packed(p, q, ne);
+        const double apq = Ap[ipq];
+        double c = 1.0, s_ = 0.0;
+        if (fabs(apq) > 1e-300) {
+          const double app = Ap[ipp], aqq = Ap[iqq];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = rsqrt(t * t + 1.0); s_ = t * c;
+          Ap[ipp] = app - t * apq; Ap[iqq] = aqq + t * apq; Ap[ipq] = 0.0;
+        }
+        cs[tid] = c; sn[tid] = s_; pp[tid] = p; qq[tid] = q;
+        log[(size_t)rounds * m + tid] = make_double2(c, s_);
+      }
+      __syncthreads();
+      for (int x = tid; x < ntask; x += nt) {
+        const unsigned short kl = pairtab[x];
+        const int k = kl >> 8, l = kl & 255;
+        const double ck = cs[k], sk = sn[k], cl = cs[l], sl = sn[l];
+        if (sk == 0.0 && sl == 0.0) continue;
+        const int p = pp[k], q = qq[k], r = pp[l], u = qq[l];
+        const int ipr = sym_packed(p, r, ne), ipu = sym_packed(p, u, ne), iqr = sym_packed(q, r, ne), iqu = sym_packed(q, u, ne);
+        const double bpr = Ap[ipr], bpu = Ap[ipu], bqr = Ap[iqr], bqu = Ap[iqu];
+        // T = B J_l
+        const double tpr = cl * bpr - sl * bpu, tpu = sl * bpr + cl * bpu;
+        const double tqr = cl * bqr - sl * bqu, tqu = sl * bqr + cl * bqu;
+        // B' = J_k^T T
+        Ap[ipr] = ck * tpr - sk * tqr; Ap[ipu] = ck * tpu - sk * tqu;
+        Ap[iqr] = sk * tpr + ck * tqr; Ap[iqu] = sk * tpu + ck * tqu;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) metaall[blockIdx.x] = rounds;
+  // ascending order by rank (the padding index of an odd n is left out)
+  for (int i = tid; i < n; i += nt) {
+    const double wi = Ap[tri_packed(i, i, ne)];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) { const double wj = Ap[tri_packed(j, j, ne)]; rank += (wj < wi) || (wj == wi && j < i); }
+    wall[(size_t)blockIdx.x * n + rank] = wi;
+    rankall[(size_t)blockIdx.x * n + i] = rank;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_jacobi_vectors(int n, const double2* __restrict__ logall, const int* __restrict__ metaall,
+                                                         const int* __restrict__ rankall, double* __restrict__ Voutall, int max_sweeps) {
+  extern __shared__ double sm[];
+  const int ne = n + (n & 1), m = ne >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const double2* log = logall + (size_t)b * max_sweeps * (ne - 1) * m;
+  const int rounds = metaall[b];
+  double* v = sm + (size_t)warp * ne;
+  for (int x = lane; x < ne; x += 32) v[x] = (x == row) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int round = rd % (ne - 1);
+    for (int k = lane; k < m; k += 32) {
+      const double2 r = log[(size_t)rd * m + k];
+      if (r.y != 0.0) {
+        int p, q; rr_pair(round, k, ne, &p, &q);
+        const double vp = v[p], vq = v[q];
+        v[p] = r.x * vp - r.y * vq; v[q] = r.y * vp + r.x * vq;
+      }
+    }
+    __syncwarp();
+  }
+  double* Vout = Voutall + (size_t)b * n * n + (size_t)row * n;
+  const int* rank = rankall + (size_t)b * n;
+  for (int x = lane; x < n; x += 32) Vout[rank[x]] = v[x];
+}
+
 // B[i,j] = A[i,j] * f(w[j]);  mode 0: w^-1/2
 __global__ void k_scale_cols_rsqrt(int n, const double* __restrict__ A, const double* __restrict__ w, double* __restrict__ B) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -762,12 +906,43 @@ void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const d
   else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
   DQ_LAUNCHED();
 }
-void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w) {
-  const int m = (n + 1) / 2;
-  const size_t smem = (size_t)2 * m * sizeof(double) + (size_t)2 * m * sizeof(int);
+constexpr int kJacobiPackedMax = 236;   // packed upper triangle + rotation arrays must fit 227 KB of shared memory
+constexpr int kJacobiSweeps = 30;
+size_t eigh_workspace_bytes(int n, int batch) {
+  const int ne = n + (n & 1), m = ne / 2;
+  size_t b = 0;
+  b += (size_t)batch * kJacobiSweeps * (ne - 1 > 0 ? ne - 1 : 1) * m * sizeof(double2);   // rotation log
+  b += (size_t)batch * n * sizeof(int) + (size_t)batch * sizeof(int) + 256;                // ranks, round counts
+  b += (size_t)(m * (m - 1) / 2 + 1) * sizeof(unsigned short) + 256;                        // pair-of-pairs table
+  return b;
+}
+void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w, void* work) {
+  if (n > kJacobiPackedMax || n < 2 || work == nullptr) {
+    const int m = (n + 1) / 2;
+    const size_t smem = (size_t)2 * m * sizeof(double) + (size_t)2 * m * sizeof(int);
+    int threads = 1024;
+    if (n <= 16) threads = 128; else if (n <= 32) threads = 256; else if (n <= 64) threads = 512;
+    k_eigh_jacobi<<<batch, threads, smem, st>>>(n, A, Vwork, Vout, w, 60); DQ_LAUNCHED();
+    return;
+  }
+  const int ne = n + (n & 1), m = ne / 2;
+  char* base = (char*)work;
+  double2* log = (double2*)base; base += (size_t)batch * kJacobiSweeps * (ne - 1) * m * sizeof(double2);
+  int* rank = (int*)base; base += (size_t)batch * n * sizeof(int);
+  int* meta = (int*)base; base += (((size_t)batch * sizeof(int) + 255) / 256) * 256;
+  unsigned short* tab = (unsigned short*)base;
+  const size_t smem1 = (size_t)(ne * (ne + 1) / 2 + 2 * m) * sizeof(double) + (size_t)2 * m * sizeof(int);
+  static size_t attr1 = 0;
+  if (smem1 > 48 * 1024 && smem1 > attr1) { cudaFuncSetAttribute(k_jacobi_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1); attr1 = smem1; }
   int threads = 1024;
-  if (n <= 16) threads = 128; else if (n <= 32) threads = 256; else if (n <= 64) threads = 512;
-  k_eigh_jacobi<<<batch, threads, smem, st>>>(n, A, Vwork, Vout, w, 60); DQ_LAUNCHED();
+  if (n <= 16) threads = 64; else if (n <= 32) threads = 128; else if (n <= 64) threads = 256; else if (n <= 128) threads = 512;
+  k_jacobi_packed<<<batch, threads, smem1, st>>>(n, A, tab, log, meta, w, rank, kJacobiSweeps); DQ_LAUNCHED();
+  int wpb = n < 32 ? n : 32;             // warps (rows) per CTA
+  const size_t smem2 = (size_t)wpb * ne * sizeof(double);
+  static size_t attr2 = 0;
+  if (smem2 > 48 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_jacobi_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); attr2 = smem2; }
+  dim3 grid((n + wpb - 1) / wpb, batch);
+  k_jacobi_vectors<<<grid, wpb * 32, smem2, st>>>(n, log, meta, rank, Vout, kJacobiSweeps); DQ_LAUNCHED();
 }
 void launch_scale_cols_rsqrt(cudaStream_t st, int n, const double* A, const double* w, double* B) {
   k_scale_cols_rsqrt<<<cdiv((long long)n * n, 256), 256, 0, st>>>(n, A, w, B); DQ_LAUNCHED();

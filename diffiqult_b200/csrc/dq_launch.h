@@ -30,7 +30,9 @@ void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, co
                      double* g_xyz);
 void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
                  int ldc, double alpha, double beta);
-void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w);
+size_t eigh_workspace_bytes(int n, int batch);
+// `work`: eigh_workspace_bytes(n, batch) bytes of device memory (NULL: slow global-memory fallback)
+void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w, void* work);
 void launch_scale_cols_rsqrt(cudaStream_t st, int n, const double* A, const double* w, double* B);
 void launch_fock_combine(cudaStream_t st, int n, const int* f_block, const double* H, const double* Jacc, const double* Kacc, double* F,
                          double* G);
