@@ -8,6 +8,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -319,27 +321,40 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   JK jk; jk.JKacc = ws.alloc<double>(2 * nn);
   double *F = ws.alloc<double>(nn), *Fp = ws.alloc<double>(nn), *U = ws.alloc<double>(nn), *C = ws.alloc<double>(nn),
          *D = ws.alloc<double>(nn), *eps = ws.alloc<double>(n), *dE = ws.alloc<double>(1);
-  // history for the reverse sweep: F_{t-1}, U_t, eps_t, D_t, F_t
+  // history for the reverse sweep: F_{t-1}, U_t, eps_t, D_t, F_t  (device slabs of 16 iterations: no per-iteration cudaMalloc)
   std::vector<double*> hFprev, hU, hEps, hD, hF;
+  double* slab = nullptr; int slab_left = 0;
+  auto hist = [&](size_t cnt) { double* p = slab; slab += cnt; return p; };
   CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));          // Energy.py:159 (core guess)
   double oldE = 1e8, e_elec = 0.0;
   out.esteps.clear();
   out.converged = false;
+  const bool trace = getenv("DQ_TRACE") != nullptr;
   for (int it = 0; it < max_scf; ++it) {
-    if (want_grad) { double* f = ws.alloc<double>(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st)); hFprev.push_back(f); }
+    double tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+    auto now = [&]() { cudaStreamSynchronize(st); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    if (trace) tr0 = now();
+    if (want_grad) {
+      if (slab_left == 0) { slab = ws.alloc<double>((size_t)16 * (4 * nn + n)); slab_left = 16; }
+      --slab_left;
+      double* f = hist(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st)); hFprev.push_back(f);
+    }
     launch_gemm(st, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
     launch_gemm(st, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
+    if (trace) tr1 = now();
     launch_eigh(st, n, 1, Fp, vwork, U, eps, ework);                                  // Energy.py:167-168
+    if (trace) tr2 = now();
     launch_gemm(st, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
     launch_gemm(st, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180
     fock_build(P, jk, D, H, F, nullptr);                                       // Energy.py:188
     launch_dot3(st, (int)nn, D, H, F, dE);                                     // Energy.py:189
     CU(cudaMemcpyAsync(&e_elec, dE, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (trace) { tr3 = now(); fprintf(stderr, "[dq trace] it %d: pre %.3f ms, eigh %.3f ms, rest %.3f ms\n", it, tr1 - tr0, tr2 - tr1, tr3 - tr2); }
     out.esteps.push_back(e_elec);
     out.niter = it + 1;
     if (want_grad) {
-      double *u = ws.alloc<double>(nn), *e = ws.alloc<double>(n), *d = ws.alloc<double>(nn), *f = ws.alloc<double>(nn);
+      double *u = hist(nn), *e = hist(n), *d = hist(nn), *f = hist(nn);
       CU(cudaMemcpyAsync(u, U, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
       CU(cudaMemcpyAsync(e, eps, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
       CU(cudaMemcpyAsync(d, D, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_packed(int n, const double* __r
     if (i <= j) Ap[tri_packed(i, j, ne)] = (i < n && j < n) ? A[i * n + j] : 0.0;
   }
   const int ntask = m * (m - 1) / 2;
+  double prev_off = 1e300;
   // table of the pairs of pairs (k < l), task x = l(l-1)/2 + k (every CTA writes the same values)
   for (int x = tid; x < ntask; x += nt) {
     int l = (int)((1.0 + sqrt(1.0 + 8.0 * x)) * 0.5);
@@ -635,7 +636,9 @@ __global__ void __launch_bounds__(1024) k_jacobi_packed(int n, const double* __r
     __syncthreads();
     if (tid == 0) { double t = 0; for (int x = 0; x < (nt + 31) / 32; ++x) t += red[x]; s_tot = t + s_off; }
     __syncthreads();
-    if (s_off <= 1e-30 * s_tot) break;
+    // converged, or stagnating at the rounding floor (off-norm already ~1e-12 relative and no longer shrinking)
+    if (s_off <= 1e-30 * s_tot || (s_off <= 1e-24 * s_tot && s_off > 0.25 * prev_off)) break;
+    prev_off = s_off;
     for (int round = 0; round < ne - 1; ++round, ++rounds) {
       if (tid < m) {
         int p, q; rr_pair(round, tid, ne, &p, &q);
@@ -682,28 +685,47 @@ __global__ void __launch_bounds__(1024) k_jacobi_packed(int n, const double* __r
   }
 }
 
-__global__ void __launch_bounds__(1024) k_jacobi_vectors(int n, const double2* __restrict__ logall, const int* __restrict__ metaall,
-                                                         const int* __restrict__ rankall, double* __restrict__ Voutall, int max_sweeps) {
+__global__ void __launch_bounds__(256) k_jacobi_vectors(int n, const double2* __restrict__ logall, const int* __restrict__ metaall,
+                                                        const int* __restrict__ rankall, double* __restrict__ Voutall, int max_sweeps) {
   extern __shared__ double sm[];
-  const int ne = n + (n & 1), m = ne >> 1;
+  const int ne = n + (n & 1), m = ne >> 1, np1 = ne - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   const int b = blockIdx.y;
   if (row >= n) return;
-  const double2* log = logall + (size_t)b * max_sweeps * (ne - 1) * m;
+  const double2* log = logall + (size_t)b * max_sweeps * np1 * m;
   const int rounds = metaall[b];
   double* v = sm + (size_t)warp * ne;
   for (int x = lane; x < ne; x += 32) v[x] = (x == row) ? 1.0 : 0.0;
   __syncwarp();
+  // each lane owns pairs k = lane, lane+32, ... (at most 4 for n <= 256); the tournament positions advance by one per round
+  constexpr int KP = 4;
+  int pa[KP], pb[KP];
+  double2 cur[KP], nxt[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    const int k = lane + 32 * j;
+    pa[j] = k % np1; pb[j] = (np1 - (k % np1)) % np1;     // round 0: a = k, b = -k (mod np1); k == 0 is the fixed player
+    cur[j] = (k < m && rounds > 0) ? log[k] : make_double2(1.0, 0.0);
+  }
   for (int rd = 0; rd < rounds; ++rd) {
-    const int round = rd % (ne - 1);
-    for (int k = lane; k < m; k += 32) {
-      const double2 r = log[(size_t)rd * m + k];
-      if (r.y != 0.0) {
-        int p, q; rr_pair(round, k, ne, &p, &q);
-        const double vp = v[p], vq = v[q];
-        v[p] = r.x * vp - r.y * vq; v[q] = r.y * vp + r.x * vq;
+    if (rd + 1 < rounds) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { const int k = lane + 32 * j; nxt[j] = k < m ? log[(size_t)(rd + 1) * m + k] : make_double2(1.0, 0.0); }
+    }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      const int k = lane + 32 * j;
+      if (k < m && cur[j].y != 0.0) {
+        const int a = (k == 0) ? ne - 1 : pa[j], bb = pb[j];
+        const double va = v[a], vb = v[bb];
+        // rotation acts on (p, q) = (min, max); swapping the roles flips the sign of s
+        const double s_ = a < bb ? cur[j].y : -cur[j].y;
+        v[a] = cur[j].x * va - s_ * vb; v[bb] = s_ * va + cur[j].x * vb;
       }
+      pa[j] = pa[j] + 1 == np1 ? 0 : pa[j] + 1;
+      pb[j] = pb[j] + 1 == np1 ? 0 : pb[j] + 1;
+      cur[j] = nxt[j];
     }
     __syncwarp();
   }
@@ -937,7 +959,7 @@ void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, do
   int threads = 1024;
   if (n <= 16) threads = 64; else if (n <= 32) threads = 128; else if (n <= 64) threads = 256; else if (n <= 128) threads = 512;
   k_jacobi_packed<<<batch, threads, smem1, st>>>(n, A, tab, log, meta, w, rank, kJacobiSweeps); DQ_LAUNCHED();
-  int wpb = n < 32 ? n : 32;             // warps (rows) per CTA
+  int wpb = n < 4 ? n : 4;               // warps (rows) per CTA: many small CTAs spread the log reads over the SMs
   const size_t smem2 = (size_t)wpb * ne * sizeof(double);
   static size_t attr2 = 0;
   if (smem2 > 48 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_jacobi_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); attr2 = smem2; }
