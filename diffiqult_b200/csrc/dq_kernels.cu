@@ -388,10 +388,10 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
         PairAdj ka; ka.P[0] = ka.P[1] = ka.P[2] = ka.g = ka.K = 0.0;
         double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
         prim_quartet<LA, LB, LC, LD, true>(bra, ket, ia, ib, ic, id, c_boys, W, &ba, &ka, &e0, &e1, &e2, &e3);
-        if (LA) { ba.P[ia] += e0; pas += e0; }
-        if (LB) { ba.P[ib] += e1; pbs += e1; }
-        if (LC) { ka.P[ic] += e2; qcs += e2; }
-        if (LD) { ka.P[id] += e3; qds += e3; }
+        if (LA) { add3(ba.P, ia, e0); pas += e0; }
+        if (LB) { add3(ba.P, ib, e1); pbs += e1; }
+        if (LC) { add3(ka.P, ic, e2); qcs += e2; }
+        if (LD) { add3(ka.P, id, e3); qds += e3; }
         double* a = sacc + (pk * kAdjFields) * 256 + tid;
         a[0] += ka.P[0]; a[256] += ka.P[1]; a[512] += ka.P[2]; a[768] += ka.g; a[1024] += ka.K;
       }
