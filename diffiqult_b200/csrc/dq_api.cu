@@ -12,6 +12,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,15 +36,57 @@ static void fail(int code, const char* fmt, const char* a = "") {
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) fail(-2, "CUDA error: %s", cudaGetErrorString(e_)); } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Device-memory pool: freed blocks are kept (per device, by exact size) and handed out again, so that repeated
+// calls on the same problem -- every BFGS step, every bench step -- do not pay cudaMalloc/cudaFree of the 2.6 GB tile
+// store.  Blocks return to the pool only after the owning call has synchronised its stream.
+struct Pool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;
+  size_t cached_bytes = 0;
+  void* get(int dev, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find({dev, bytes});
+      if (it != free_blocks.end()) { void* p = it->second; free_blocks.erase(it); cached_bytes -= bytes; return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {          // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      release();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return nullptr;
+    return p;
+  }
+  void put(int dev, size_t bytes, void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    free_blocks.insert({{dev, bytes}, p});
+    cached_bytes += bytes;
+  }
+  void release() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+static Pool g_pool;
+
 struct Workspace {
   cudaStream_t st = 0;
-  std::vector<void*> owned;
-  ~Workspace() { for (void* p : owned) cudaFree(p); }
+  int dev = 0;
+  std::vector<std::pair<void*, size_t>> owned;
+  ~Workspace() {
+    cudaStreamSynchronize(st);
+    for (auto& b : owned) g_pool.put(dev, b.second, b.first);
+  }
   template <class T> T* alloc(size_t n, bool zero = false) {
-    void* p = nullptr;
     if (n == 0) n = 1;
-    CU(cudaMalloc(&p, n * sizeof(T)));
-    owned.push_back(p);
+    const size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+    void* p = g_pool.get(dev, bytes);
+    if (!p) fail(-2, "CUDA error: %s", "out of device memory");
+    owned.push_back({p, bytes});
     if (zero) CU(cudaMemsetAsync(p, 0, n * sizeof(T), st));
     return (T*)p;
   }
@@ -100,6 +144,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
   CU(cudaSetDevice(dev));
+  P.ws.dev = dev;
   P.ws.st = opt ? (cudaStream_t)opt->stream : 0;
   cudaStream_t st = P.ws.st;
   P.world = (opt && opt->world_size > 1) ? opt->world_size : 1;
@@ -472,6 +517,7 @@ extern "C" {
 
 const char* dq_last_error(void) { return t_err.c_str(); }
 void dq_get_stats(dq_stats* out) { if (out) *out = t_stats; }
+void dq_release_cache(void) { g_pool.release(); }
 int dq_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 int dq_normalization(const dq_system* sys, const dq_options* opt, double* out) {
@@ -586,7 +632,7 @@ int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
   CU(cudaSetDevice(device));
   reset_launch_count();
-  Workspace ws;
+  Workspace ws; ws.dev = device;
   const size_t nn = (size_t)n * n * batch;
   double *dA = ws.alloc<double>(nn), *dW = ws.alloc<double>(nn), *dV = ws.alloc<double>(nn), *dw = ws.alloc<double>((size_t)n * batch);
   CU(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
@@ -604,7 +650,7 @@ int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
   CU(cudaSetDevice(device));
   if (upload_boys_constants() != 0) fail(-2, "constant upload failed");
-  Workspace ws;
+  Workspace ws; ws.dev = device;
   double *dt = ws.alloc<double>(n), *dF_ = ws.alloc<double>((size_t)5 * n), *ddF = ws.alloc<double>((size_t)5 * n);
   CU(cudaMemcpy(dt, t, n * sizeof(double), cudaMemcpyHostToDevice));
   launch_boys(0, n, dt, dF_, ddF);
@@ -619,7 +665,7 @@ int dq_fp64_peak(int32_t device, double* tflops) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
   CU(cudaSetDevice(device));
   cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
-  Workspace ws;
+  Workspace ws; ws.dev = device;
   double* out = ws.alloc<double>(1);
   const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
   launch_fp64_peak(0, blocks, 1024, out);

@@ -343,8 +343,9 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
 //   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
 // where sum_terms <A, dG[B]> is the two-electron part of dE from the SCF reverse sweep.
 // ---------------------------------------------------------------------------------------------
+// occupancy: the light classes (at most two p functions) fit two CTAs per SM (<= 128 registers, 2 x 112 KB shared memory)
 template <bool LA, bool LB, bool LC, bool LD>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 2) ? 2 : 1)
 k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd, int nterms,
                  const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
                  double* __restrict__ pasum) {

@@ -106,6 +106,8 @@ int dq_fp64_peak(int32_t device, double* tflops);
 void dq_get_stats(dq_stats* out);       /* stats of the last call made by this thread */
 const char* dq_last_error(void);        /* message of the last non-zero status of this thread */
 int dq_device_count(void);
+/* device buffers are pooled between calls (same-size reuse); this returns them to the driver */
+void dq_release_cache(void);
 
 #ifdef __cplusplus
 }
