@@ -38,7 +38,7 @@ class dq_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["dq_normalization", "dq_one_electron", "dq_eri_packed", "dq_fock", "dq_rhf", "dq_rhf_grad", "dq_eigh",
+EXPORTS = ["dq_plan", "dq_normalization", "dq_one_electron", "dq_eri_packed", "dq_fock", "dq_rhf", "dq_rhf_grad", "dq_eigh",
            "dq_boys", "dq_fp64_peak", "dq_get_stats", "dq_last_error", "dq_device_count", "dq_release_cache"]
 
 _lib = None
@@ -72,6 +72,13 @@ def stats():
     s = dq_stats()
     lib().dq_get_stats(C.byref(s))
     return s.as_dict()
+
+
+def plan(sysarrays, world_size=1, rank=0):
+    """Host-only work decomposition of one rank: dict(blocks, block_pairs, tiles, quartets, prim_quartets, tiles_total)."""
+    out = (C.c_int64 * 6)()
+    check(lib().dq_plan(C.byref(sysarrays.struct), C.c_int32(world_size), C.c_int32(rank), out))
+    return dict(zip(("blocks", "block_pairs", "tiles", "quartets", "prim_quartets", "tiles_total"), [int(x) for x in out]))
 
 
 def _f(a):

@@ -122,9 +122,17 @@ struct Prepared {
   int2* d_chunks = nullptr; int nchunks = 0;   // runs of tiles sharing the bra block pair (J/K contraction)
   double* d_store = nullptr;
   bool log_alpha = false;
+  bool plan_only = false;       // host planning only (dq_plan): no CUDA call is made
   int world = 1, rank = 0;
   dq_allreduce_fn allreduce = nullptr; void* ar_user = nullptr;
 };
+
+static void need_device(int dev) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); fail(-3, "no CUDA device: diffiqult_b200 has no CPU path"); }
+  if (dev < 0 || dev >= ndev) fail(-1, "device ordinal out of range");
+  CU(cudaSetDevice(dev));
+}
 
 static void check_system(const dq_system* s) {
   if (!s) fail(-1, "null system");
@@ -142,8 +150,8 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   check_system(s);
   int dev = opt ? opt->device : 0;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
-  CU(cudaSetDevice(dev));
+  (void)ndev;
+  if (!P.plan_only) need_device(dev);
   P.ws.dev = dev;
   P.ws.st = opt ? (cudaStream_t)opt->stream : 0;
   cudaStream_t st = P.ws.st;
@@ -153,7 +161,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   P.ar_user = opt ? opt->allreduce_user : nullptr;
   if (P.world > 1 && !P.allreduce) fail(-1, "world_size > 1 needs an allreduce callback");
   static thread_local int boys_dev = -1;
-  if (boys_dev != dev) { if (upload_boys_constants() != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
+  if (!P.plan_only && boys_dev != dev) { if (upload_boys_constants() != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
 
   const int N = s->nbasis;
   P.N = N; P.nprim = s->nprim; P.ne = s->ne; P.log_alpha = s->log_alpha != 0;
@@ -214,6 +222,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
 
   // device copies
   Workspace& ws = P.ws;
+  if (!P.plan_only) {
   P.d_foff = ws.upload(foff); P.d_ftype = ws.upload(ftype); P.d_fblock = ws.upload(fblock); P.d_forig = ws.upload(P.f_orig);
   P.d_xyz = ws.upload(xyz); P.d_craw = ws.upload(craw);
   std::vector<int> Z(s->natoms > 0 ? s->natoms : 1, 0);
@@ -238,6 +247,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
   sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
+  }
 
   if (!need_tiles) return;
   // tiles of this rank, grouped by angular class (pI pJ | pK pL)
@@ -257,6 +267,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   P.tiles.clear();
   for (int c = 0; c < 16; ++c) { P.cls_start[c] = (int)P.tiles.size(); P.tiles.insert(P.tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
   P.cls_start[16] = (int)P.tiles.size();
+  if (P.plan_only) return;
   P.d_tiles = ws.upload(P.tiles);
   {
     constexpr int kChunk = 256;
@@ -273,7 +284,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
     if (((size_t)16 * N + 2 * 16 * 17 + 16) * sizeof(double) > 220 * 1024) fail(-1, "basis too large for the J/K kernel's shared-memory row strips");
   }
   P.d_pd = ws.alloc<double>(P.pd_len);
-  launch_pairs(st, sd, P.d_pd);
+  launch_pairs(st, P.sd, P.d_pd);
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
@@ -331,7 +342,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   const double tol = (opt && opt->e_tol > 0) ? opt->e_tol : 1e-8;
   if (s->ne <= 0 || s->ne > s->nbasis) fail(-1, "ne (doubly-occupied orbitals) must be in 1..nbasis");
   cudaStream_t st0 = opt ? (cudaStream_t)opt->stream : 0;
-  CU(cudaSetDevice(opt ? opt->device : 0));
+  need_device(opt ? opt->device : 0);
   Timer t_total(st0);
   Timer t_setup(st0);
   prepare(P, s, opt, true, true);
@@ -520,6 +531,22 @@ void dq_get_stats(dq_stats* out) { if (out) *out = t_stats; }
 void dq_release_cache(void) { g_pool.release(); }
 int dq_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
+// host-only view of the work decomposition (no GPU needed): out = {function blocks, block pairs, tiles of this rank,
+// contracted quartets of this rank, primitive quartets of this rank, tiles of all ranks}
+int dq_plan(const dq_system* sys, int32_t world_size, int32_t rank, int64_t* out) {
+  DQ_TRY
+  if (world_size < 1 || rank < 0 || rank >= world_size) fail(-1, "bad world_size / rank");
+  Prepared P;
+  P.plan_only = true;
+  dq_options o; memset(&o, 0, sizeof o);
+  o.world_size = world_size; o.rank = rank;
+  o.allreduce = (dq_allreduce_fn)(void*)1;   // never called in plan mode
+  prepare(P, sys, &o, true, false);
+  out[0] = P.nblocks; out[1] = P.nbp; out[2] = (int64_t)P.tiles.size(); out[3] = P.n_quartets; out[4] = P.n_prim_quartets;
+  out[5] = (int64_t)P.nbp * (P.nbp + 1) / 2;
+  DQ_CATCH
+}
+
 int dq_normalization(const dq_system* sys, const dq_options* opt, double* out) {
   DQ_TRY
   memset(&t_stats, 0, sizeof t_stats); reset_launch_count();
@@ -628,9 +655,7 @@ int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t*
 
 int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int32_t device) {
   DQ_TRY
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
-  CU(cudaSetDevice(device));
+  need_device(device);
   reset_launch_count();
   Workspace ws; ws.dev = device;
   const size_t nn = (size_t)n * n * batch;
@@ -646,9 +671,7 @@ int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int
 
 int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device) {
   DQ_TRY
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
-  CU(cudaSetDevice(device));
+  need_device(device);
   if (upload_boys_constants() != 0) fail(-2, "constant upload failed");
   Workspace ws; ws.dev = device;
   double *dt = ws.alloc<double>(n), *dF_ = ws.alloc<double>((size_t)5 * n), *ddF = ws.alloc<double>((size_t)5 * n);
@@ -661,9 +684,7 @@ int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device) {
 
 int dq_fp64_peak(int32_t device, double* tflops) {
   DQ_TRY
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(-3, "no CUDA device: diffiqult_b200 has no CPU path");
-  CU(cudaSetDevice(device));
+  need_device(device);
   cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
   Workspace ws; ws.dev = device;
   double* out = ws.alloc<double>(1);

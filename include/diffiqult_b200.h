@@ -65,6 +65,11 @@ typedef struct dq_stats {
   int32_t grad_terms;      /* rank of the two-particle weight used by the ERI-gradient pass */
 } dq_stats;
 
+/* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):
+ * out[6] = {function blocks, block pairs, tiles of this rank, contracted quartets of this rank, primitive
+ * quartets of this rank, tiles of all ranks}.  Replaces the loop nest of Integrals.py:190-216 (erivector). */
+int dq_plan(const dq_system* sys, int32_t world_size, int32_t rank, int64_t* out);
+
 /* Integrals.py:477-501 normalization(alpha, c, l, list_contr): sys->coef raw -> out[nprim] */
 int dq_normalization(const dq_system* sys, const dq_options* opt, double* out);
 
