@@ -237,3 +237,47 @@ def test_water_dimer_energy_and_gradient_vs_oracle():
         og = orc.rhf_grad(a, n, max_scf=100)
         assert og["status"] == 0
         assert np.abs(r["grad"][n] - og["grad"]).max() < TOL_G
+
+
+def test_two_rank_sharding_emulated_on_one_gpu():
+    """The N>1 path on a single GPU: two host threads play rank 0 and rank 1 (each computes its half of the ERI tiles),
+    the allreduce callback sums their device buffers through the host.  No kernel waits on another kernel: the host
+    threads wait, with their streams idle.  Results must equal the single-rank run."""
+    import threading
+    import torch
+    from diffiqult_b200 import distributed
+    s = sysmol("ch2o")
+    args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+    ref = Energy.rhf_grad(*args, max_scf=100)
+    world = 2
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+
+    def make_cb(rank):
+        def _cb(ptr, count, user):
+            t = torch.as_tensor(distributed._CudaBuffer(ptr, count), device="cuda:0")
+            torch.cuda.synchronize()
+            slots[rank] = t.cpu()
+            barrier.wait()
+            total = slots[0] + slots[1]
+            barrier.wait()
+            t.copy_(total.cuda())
+            torch.cuda.synchronize()
+        return _capi.ALLREDUCE_FN(_cb)
+
+    def run(rank):
+        cb = make_cb(rank)
+        results[rank] = Energy.rhf_grad(*args, max_scf=100, world_size=world, rank=rank, allreduce=cb)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for r in results:
+        assert r is not None and r["status"] == 0 and r["niter"] == ref["niter"]
+        assert abs(r["E"] - ref["E"]) < 1e-10
+        for n in range(3):
+            assert np.abs(r["grad"][n] - ref["grad"][n]).max() < 1e-9
+    assert results[0]["stats"]["n_tiles"] + results[1]["stats"]["n_tiles"] == ref["stats"]["n_tiles"]
