@@ -398,7 +398,18 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     launch_gemm(st, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
     launch_gemm(st, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
     if (trace) tr1 = now();
-    launch_eigh(st, n, 1, Fp, vwork, U, eps, ework);                                  // Energy.py:167-168
+    // Energy.py:167-168.  Warm start: successive Fock matrices are close, so F' is first rotated into the previous
+    // iteration's eigenbasis (nearly diagonal -> Jacobi converges in 2-4 sweeps instead of ~9); U = U_prev V.
+    if (it == 0 || getenv("DQ_COLD_EIGH")) {
+      launch_eigh(st, n, 1, Fp, vwork, U, eps, ework);
+    } else {
+      launch_gemm(st, true, false, n, n, n, U, n, Fp, n, t1, n, 1.0, 0.0);      // U_prev^T F'
+      launch_gemm(st, false, false, n, n, n, t1, n, U, n, t2, n, 1.0, 0.0);     // U_prev^T F' U_prev
+      launch_symmetrize(st, n, t2);
+      launch_eigh(st, n, 1, t2, vwork, t3, eps, ework);
+      launch_gemm(st, false, false, n, n, n, U, n, t3, n, t1, n, 1.0, 0.0);     // U_prev V
+      CU(cudaMemcpyAsync(U, t1, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
     if (trace) tr2 = now();
     launch_gemm(st, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
     launch_gemm(st, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180

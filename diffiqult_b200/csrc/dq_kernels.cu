@@ -284,15 +284,25 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
   const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
   if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
   double jacc = 0.0;
+  // software pipeline: the next tile's block pair, ERI value and D_kl are in flight while the current tile is digested
+  int nbp2 = tiles[ch.x].bp2;
+  BlockPair nb2 = s.bp[nbp2];
+  double nv = store[(long long)ch.x * kTile + tid];
+  double ndkl = (kl < nb2.nI && ll < nb2.nJ) ? D[(nb2.sI + kl) * n + nb2.sJ + ll] : 0.0;
   __syncthreads();
   for (int t = 0; t < ch.y; ++t) {
-    const int ti = ch.x + t;
-    const int bp2 = tiles[ti].bp2;
-    const BlockPair b2 = s.bp[bp2];
-    const double v = store[(long long)ti * kTile + tid];
+    const int bp2 = nbp2;
+    const BlockPair b2 = nb2;
+    const double v = nv, dkl = ndkl;
+    if (t + 1 < ch.y) {
+      const int ti1 = ch.x + t + 1;
+      nbp2 = tiles[ti1].bp2;
+      nb2 = s.bp[nbp2];
+      nv = store[(long long)ti1 * kTile + tid];
+      ndkl = (kl < nb2.nI && ll < nb2.nJ) ? D[(nb2.sI + kl) * n + nb2.sJ + ll] : 0.0;
+    }
     const bool dKL = b2.bI == b2.bJ;
     const double wS = bp1 == bp2 ? 0.5 : 1.0;
-    const double dkl = (kl < b2.nI && ll < b2.nJ) ? D[(b2.sI + kl) * n + b2.sJ + ll] : 0.0;
     jacc += (wS * (dKL ? 1.0 : 2.0)) * dkl * v;
     double* svb = sv + (t & 1) * (16 * 17);
     svb[bl * 17 + kt] = v;
@@ -646,8 +656,12 @@ __global__ void __launch_bounds__(1024) k_jacobi_packed(int n, const double* __r
         const int ipp = tri_packed(p, p, ne), iqq = tri_packed(q, q, ne), ipq = tri_packed(p, q, ne);
         const double apq = Ap[ipq];
         double c = 1.0, s_ = 0.0;
-        if (fabs(apq) > 1e-300) {
-          const double app = Ap[ipp], aqq = Ap[iqq];
+        const double app = Ap[ipp], aqq = Ap[iqq];
+        // a rotation by less than ~1e-18 rad changes nothing representable: drop the element instead (Numerical
+        // Recipes' jacobi does the same); lets the last sweep of a warm-started solve skip its block updates
+        if (fabs(apq) <= 1e-18 * (fabs(app) + fabs(aqq))) {
+          Ap[ipq] = 0.0;
+        } else {
           const double theta = (aqq - app) / (2.0 * apq);
           const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
           c = rsqrt(t * t + 1.0); s_ = t * c;
