@@ -21,7 +21,7 @@
 namespace dq {
 
 __constant__ BoysConst c_boys;
-static long long g_launches = 0;   // kernels launched by this library (reported by dq_stats)
+static thread_local long long g_launches = 0;   // kernels launched by this host thread (reported by dq_stats)
 
 long long launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
 // ---------------------------------------------------------------------------------------------
 // occupancy: the light classes (at most two p functions) fit two CTAs per SM (<= 128 registers, 2 x 112 KB shared memory)
 template <bool LA, bool LB, bool LC, bool LD>
-__global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
 k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd, int nterms,
                  const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
                  double* __restrict__ pasum) {

@@ -281,3 +281,52 @@ def test_two_rank_sharding_emulated_on_one_gpu():
         for n in range(3):
             assert np.abs(r["grad"][n] - ref["grad"][n]).max() < 1e-9
     assert results[0]["stats"]["n_tiles"] + results[1]["stats"]["n_tiles"] == ref["stats"]["n_tiles"]
+
+
+def test_perturbed_methane_batch_vs_oracle():
+    """BASELINE config 5 in miniature: 12 of the 1024 perturbed CH4 / STO-3G molecules, energy + full gradient through
+    the threaded batch driver (per-thread streams), against the oracle's forward-mode gradient."""
+    from diffiqult_b200 import batch
+    mols = synthetic.perturbed_methanes(12)
+    syss = [System_mol(m, basis_set_3G_STO, 10, "ch4_%d" % i) for i, m in enumerate(mols)]
+    E, status, grads = batch.rhf_grad_batch(syss, max_scf=50, threads=4)
+    assert (status == 0).all()
+    for i in (0, 5, 11):
+        a = orc.SysArrays(syss[i])
+        o = orc.rhf(a, max_scf=50)
+        assert abs(E[i] - o["E"]) < TOL_E
+        for n in (0, 1, 2):
+            og = orc.rhf_grad(a, n, max_scf=50)
+            if og["status"] == 0:
+                assert np.abs(grads[i][n] - og["grad"]).max() < TOL_G
+    # serial evaluation gives the same numbers (thread safety of the library)
+    r = Energy.rhf_grad(np.log(syss[3].alpha), syss[3].coef, syss[3].xyz, syss[3].l, syss[3].charges, syss[3].atom,
+                        syss[3].list_contr, syss[3].ne, max_scf=50)
+    assert abs(r["E"] - E[3]) < 1e-11 and np.abs(r["grad"][2] - grads[3][2]).max() < 1e-10
+    assert list(batch.shard(1024, 8, 3)) == list(range(384, 512))
+
+
+def test_full_size_cluster_properties():
+    """(H2O)_32 / STO-3G, the bench workload, through size-independent properties: convergence and iteration count,
+    directional derivative of the same truncated-SCF energy, and run-to-run reproducibility."""
+    import bench
+    s = bench.workload(32)
+    args = [np.log(s.alpha), np.array(s.coef), np.array(s.xyz)]
+    r = Energy.rhf_grad(*args, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100)
+    assert r["status"] == 0 and r["niter"] == 13
+    assert abs(r["E"] - (-2398.5489189099)) < 1e-8
+    r2 = Energy.rhf_grad(*args, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100)
+    assert abs(r["E"] - r2["E"]) < 1e-10 and max(np.abs(a - b).max() for a, b in zip(r["grad"], r2["grad"])) < 1e-9
+    rng = np.random.default_rng(11)
+    for n, h in ((0, 1e-4), (2, 1e-4)):
+        d = rng.normal(size=args[n].shape)
+        e = []
+        for sgn in (+1, -1):
+            a2 = [x.copy() for x in args]
+            a2[n] = a2[n] + sgn * h * d
+            rr = Energy.rhf(*a2, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100)
+            assert rr["niter"] == r["niter"]
+            e.append(rr["E"])
+        fd = (e[0] - e[1]) / (2 * h)
+        an = float(np.dot(r["grad"][n].ravel(), d.ravel()))
+        assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (n, fd, an)
