@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -103,6 +104,22 @@ struct Timer {
   double stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
 };
 
+// Tile lists depend only on the basis STRUCTURE (types, contraction lengths) and on (world, rank), not on the
+// parameter values: each host thread keeps the last plan, so the repeated calls of an optimisation or of the bench
+// neither rebuild nor re-upload the 1.27 M-entry tile list.
+struct TilePlan {
+  int dev = 0, world = 1, rank = 0;
+  std::vector<int> ltype, contr;
+  std::vector<Tile> tiles;      // this rank's tiles, grouped by class
+  std::vector<int2> chunks;     // runs of tiles sharing the bra block pair (J/K contraction)
+  int cls_start[17];
+  long long n_quartets = 0, n_prim_quartets = 0;
+  Tile* d_tiles = nullptr;
+  int2* d_chunks = nullptr;
+  ~TilePlan() { if (d_tiles) cudaFree(d_tiles); if (d_chunks) cudaFree(d_chunks); }
+};
+static thread_local std::shared_ptr<TilePlan> t_plan;
+
 // the sorted / blocked system on the device plus the maps back to the caller's ordering
 struct Prepared {
   Workspace ws;
@@ -111,15 +128,16 @@ struct Prepared {
   std::vector<int> f_orig;      // sorted function -> original function
   std::vector<int> p_orig;      // sorted primitive -> original primitive
   std::vector<BlockPair> bps;
-  std::vector<Tile> tiles;      // this rank's tiles, grouped by class
-  int cls_start[17];
+  std::shared_ptr<TilePlan> tp;
   long long pd_len = 0;         // doubles in the pair-record buffer
   long long n_quartets = 0, n_prim_quartets = 0;
   // device arrays
   double *d_alpha = nullptr, *d_lnalpha = nullptr, *d_craw = nullptr, *d_cn = nullptr, *d_xyz = nullptr, *d_pd = nullptr;
   int *d_foff = nullptr, *d_ftype = nullptr, *d_fblock = nullptr, *d_forig = nullptr;
   Tile* d_tiles = nullptr;
-  int2* d_chunks = nullptr; int nchunks = 0;   // runs of tiles sharing the bra block pair (J/K contraction)
+  int2* d_chunks = nullptr; int nchunks = 0;
+  const int* cls_start = nullptr;
+  size_t ntiles = 0;
   double* d_store = nullptr;
   bool log_alpha = false;
   bool plan_only = false;       // host planning only (dq_plan): no CUDA call is made
@@ -251,45 +269,59 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
 
   if (!need_tiles) return;
   // tiles of this rank, grouped by angular class (pI pJ | pK pL)
-  std::vector<std::vector<Tile>> by_cls(16);
-  std::vector<long long> seen(16, 0);
-  for (int b1 = 0; b1 < P.nbp; ++b1) {
-    const BlockPair& x = P.bps[b1];
-    for (int b2 = b1; b2 < P.nbp; ++b2) {
-      const BlockPair& y = P.bps[b2];
-      const int cls = (x.axI >= 0) * 8 + (x.axJ >= 0) * 4 + (y.axI >= 0) * 2 + (y.axJ >= 0);
-      if (seen[cls]++ % P.world != P.rank) continue;
-      by_cls[cls].push_back({b1, b2});
-      const long long nq = (long long)x.nI * x.nJ * y.nI * y.nJ;
-      P.n_quartets += nq; P.n_prim_quartets += nq * x.KK * y.KK;
+  std::shared_ptr<TilePlan> tp = t_plan;
+  const bool hit = !P.plan_only && tp && tp->dev == dev && tp->world == P.world && tp->rank == P.rank &&
+                   tp->ltype.size() == (size_t)N && std::equal(tp->ltype.begin(), tp->ltype.end(), s->ltype) &&
+                   std::equal(tp->contr.begin(), tp->contr.end(), s->contr);
+  if (!hit) {
+    tp = std::make_shared<TilePlan>();
+    tp->dev = dev; tp->world = P.world; tp->rank = P.rank;
+    tp->ltype.assign(s->ltype, s->ltype + N); tp->contr.assign(s->contr, s->contr + N);
+    std::vector<std::vector<Tile>> by_cls(16);
+    std::vector<long long> seen(16, 0);
+    for (int b1 = 0; b1 < P.nbp; ++b1) {
+      const BlockPair& x = P.bps[b1];
+      for (int b2 = b1; b2 < P.nbp; ++b2) {
+        const BlockPair& y = P.bps[b2];
+        const int cls = (x.axI >= 0) * 8 + (x.axJ >= 0) * 4 + (y.axI >= 0) * 2 + (y.axJ >= 0);
+        if (seen[cls]++ % P.world != P.rank) continue;
+        by_cls[cls].push_back({b1, b2});
+        const long long nq = (long long)x.nI * x.nJ * y.nI * y.nJ;
+        tp->n_quartets += nq; tp->n_prim_quartets += nq * x.KK * y.KK;
+      }
     }
-  }
-  P.tiles.clear();
-  for (int c = 0; c < 16; ++c) { P.cls_start[c] = (int)P.tiles.size(); P.tiles.insert(P.tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
-  P.cls_start[16] = (int)P.tiles.size();
-  if (P.plan_only) return;
-  P.d_tiles = ws.upload(P.tiles);
-  {
+    for (int c = 0; c < 16; ++c) { tp->cls_start[c] = (int)tp->tiles.size(); tp->tiles.insert(tp->tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
+    tp->cls_start[16] = (int)tp->tiles.size();
     constexpr int kChunk = 256;
-    std::vector<int2> chunks;
     for (int c = 0; c < 16; ++c)
-      for (int t = P.cls_start[c]; t < P.cls_start[c + 1];) {
+      for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
         int e = t + 1;
-        while (e < P.cls_start[c + 1] && e - t < kChunk && P.tiles[e].bp1 == P.tiles[t].bp1) ++e;
-        chunks.push_back(make_int2(t, e - t));
+        while (e < tp->cls_start[c + 1] && e - t < kChunk && tp->tiles[e].bp1 == tp->tiles[t].bp1) ++e;
+        tp->chunks.push_back(make_int2(t, e - t));
         t = e;
       }
-    P.nchunks = (int)chunks.size();
-    P.d_chunks = ws.upload(chunks);
-    if (((size_t)16 * N + 2 * 16 * 17 + 16) * sizeof(double) > 220 * 1024) fail(-1, "basis too large for the J/K kernel's shared-memory row strips");
+    if (!P.plan_only) {
+      CU(cudaMalloc(&tp->d_tiles, std::max<size_t>(tp->tiles.size(), 1) * sizeof(Tile)));
+      CU(cudaMalloc(&tp->d_chunks, std::max<size_t>(tp->chunks.size(), 1) * sizeof(int2)));
+      CU(cudaMemcpyAsync(tp->d_tiles, tp->tiles.data(), tp->tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(tp->d_chunks, tp->chunks.data(), tp->chunks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      t_plan = tp;
+    }
   }
+  P.tp = tp;
+  P.n_quartets = tp->n_quartets; P.n_prim_quartets = tp->n_prim_quartets;
+  P.cls_start = tp->cls_start; P.ntiles = tp->tiles.size();
+  if (P.plan_only) return;
+  P.d_tiles = tp->d_tiles; P.d_chunks = tp->d_chunks; P.nchunks = (int)tp->chunks.size();
+  if (((size_t)16 * N + 2 * 16 * 17 + 16) * sizeof(double) > 220 * 1024) fail(-1, "basis too large for the J/K kernel's shared-memory row strips");
   P.d_pd = ws.alloc<double>(P.pd_len);
   launch_pairs(st, P.sd, P.d_pd);
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
 static void compute_eri_store(Prepared& P) {
-  P.d_store = P.ws.alloc<double>((size_t)P.tiles.size() * kTile);
+  P.d_store = P.ws.alloc<double>((size_t)P.ntiles * kTile);
   for (int c = 0; c < 16; ++c)
     launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
                      P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
@@ -351,7 +383,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   const int n = P.N, ne = P.ne;
   const size_t nn = (size_t)n * n;
   t_stats.ms_setup = t_setup.stop();
-  t_stats.n_tiles = (int64_t)P.tiles.size(); t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
+  t_stats.n_tiles = (int64_t)P.ntiles; t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
 
   Timer t_1e(st);
   double *S = ws.alloc<double>(nn), *T = ws.alloc<double>(nn), *V = ws.alloc<double>(nn), *H = ws.alloc<double>(nn);
@@ -539,7 +571,7 @@ extern "C" {
 
 const char* dq_last_error(void) { return t_err.c_str(); }
 void dq_get_stats(dq_stats* out) { if (out) *out = t_stats; }
-void dq_release_cache(void) { g_pool.release(); }
+void dq_release_cache(void) { g_pool.release(); t_plan.reset(); }
 int dq_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 // host-only view of the work decomposition (no GPU needed): out = {function blocks, block pairs, tiles of this rank,
@@ -553,7 +585,7 @@ int dq_plan(const dq_system* sys, int32_t world_size, int32_t rank, int64_t* out
   o.world_size = world_size; o.rank = rank;
   o.allreduce = (dq_allreduce_fn)(void*)1;   // never called in plan mode
   prepare(P, sys, &o, true, false);
-  out[0] = P.nblocks; out[1] = P.nbp; out[2] = (int64_t)P.tiles.size(); out[3] = P.n_quartets; out[4] = P.n_prim_quartets;
+  out[0] = P.nblocks; out[1] = P.nbp; out[2] = (int64_t)P.ntiles; out[3] = P.n_quartets; out[4] = P.n_prim_quartets;
   out[5] = (int64_t)P.nbp * (P.nbp + 1) / 2;
   DQ_CATCH
 }
@@ -600,11 +632,11 @@ int dq_eri_packed(const dq_system* sys, const dq_options* opt, double* eri) {
   t_stats.ms_eri = t.stop();
   const long long n = P.N, m = n * (n + 1) / 2, len = m * (m + 1) / 2;
   double* dpk = P.ws.alloc<double>(len, true);
-  launch_scatter_packed(P.ws.st, P.d_tiles, (int)P.tiles.size(), P.sd, P.d_forig, P.d_store, dpk);
+  launch_scatter_packed(P.ws.st, P.d_tiles, (int)P.ntiles, P.sd, P.d_forig, P.d_store, dpk);
   if (P.world > 1) P.allreduce(dpk, len, P.ar_user);
   CU(cudaMemcpyAsync(eri, dpk, len * sizeof(double), cudaMemcpyDeviceToHost, P.ws.st));
   CU(cudaStreamSynchronize(P.ws.st));
-  t_stats.n_tiles = (int64_t)P.tiles.size(); t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
+  t_stats.n_tiles = (int64_t)P.ntiles; t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
   t_stats.launches = launch_count();
   DQ_CATCH
 }

@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
 //   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
 // where sum_terms <A, dG[B]> is the two-electron part of dE from the SCF reverse sweep.
 // ---------------------------------------------------------------------------------------------
-// occupancy: the light classes (at most two p functions) fit two CTAs per SM (<= 128 registers, 2 x 112 KB shared memory)
+// occupancy: up to three p functions the kernel fits two CTAs per SM (128 registers with <= 40 B of spills, 2 x 112 KB
+// shared memory); (pp|pp) needs 226 registers and gains nothing from being squeezed (measured)
 template <bool LA, bool LB, bool LC, bool LD>
 __global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
 k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd, int nterms,
@@ -874,14 +875,22 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr = true;
+  }
   k_eri_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
 }
 template <bool A, bool B, bool C, bool D>
 static void grad_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
                         const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs x 112 KB
+    attr = true;
+  }
   k_eri_grad_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
 }
 
