@@ -11,6 +11,7 @@
 //   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -261,77 +262,86 @@ __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__
 //   K[i,k], K[j,k], K[i,l], K[j,l]    accumulated in two shared-memory row strips K[I,:], K[J,:], flushed once
 // with D[I,:], D[J,:] staged in shared memory.  Diagonal tiles carry weights 1/2 so that every tile is treated
 // uniformly (final J: upper block triangle mirrored; final K = Kacc + Kacc^T; DESIGN.md "Fock build").
+struct JkDesc { int sK, sL; short nK, nL; short same_bp, dKL; };   // ket block pair of one tile, 16 bytes
+
 __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
                                                    const double* __restrict__ store, const double* __restrict__ D,
                                                    double* __restrict__ Jacc, double* __restrict__ Kacc) {
   extern __shared__ double sm[];
   const int n = s.N, tid = threadIdx.x;
-  double* dstrip = sm;                  // [8][n]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
-  double* kstrip = sm + 8 * n;          // [8][n]
-  double* sv = kstrip + 8 * n;          // [2][16*17]
+  const int ns = n | 1;                 // odd row stride: the 4 rows of a strip fall into different banks
+  double* dstrip = sm;                  // [8][ns]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
+  double* kstrip = sm + 8 * ns;         // [8][ns]
+  double* sv = kstrip + 8 * ns;         // [2][16*17]
   double* sdij = sv + 2 * 16 * 17;      // [16]
+  JkDesc* desc = (JkDesc*)(sdij + 16);  // [256] ket descriptors of the chunk (breaks the tile -> block pair -> D load chain)
   const int2 ch = chunks[blockIdx.x];
   const int bp1 = tiles[ch.x].bp1;
   const BlockPair b1 = s.bp[bp1];
   const bool dIJ = b1.bI == b1.bJ;
-  for (int x = tid; x < 8 * n; x += 256) {
-    const int row = x / n, col = x - row * n, r = row & 3;
+  if (tid < ch.y) {
+    const int bp2 = tiles[ch.x + tid].bp2;
+    const BlockPair b2 = s.bp[bp2];
+    JkDesc d; d.sK = b2.sI; d.sL = b2.sJ; d.nK = (short)b2.nI; d.nL = (short)b2.nJ; d.same_bp = bp2 == bp1; d.dKL = b2.bI == b2.bJ;
+    desc[tid] = d;
+  }
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
     const bool isJ = row >= 4;
-    const bool ok = r < (isJ ? b1.nJ : b1.nI);
+    const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
     dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
     kstrip[x] = 0.0;
   }
   const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
   if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
   double jacc = 0.0;
-  // software pipeline: the next tile's block pair, ERI value and D_kl are in flight while the current tile is digested
-  int nbp2 = tiles[ch.x].bp2;
-  BlockPair nb2 = s.bp[nbp2];
-  double nv = store[(long long)ch.x * kTile + tid];
-  double ndkl = (kl < nb2.nI && ll < nb2.nJ) ? D[(nb2.sI + kl) * n + nb2.sJ + ll] : 0.0;
   __syncthreads();
+  // software pipeline, depth 2: ERI value and D_kl of tiles t+1, t+2 are in flight while tile t is digested
+  auto load_dkl = [&](int t) {
+    const JkDesc d = desc[t];
+    return (kl < d.nK && ll < d.nL) ? D[(d.sK + kl) * n + d.sL + ll] : 0.0;
+  };
+  double v1 = store[(long long)ch.x * kTile + tid], d1 = load_dkl(0), v2 = 0.0, d2 = 0.0;
+  if (ch.y > 1) { v2 = store[(long long)(ch.x + 1) * kTile + tid]; d2 = load_dkl(1); }
   for (int t = 0; t < ch.y; ++t) {
-    const int bp2 = nbp2;
-    const BlockPair b2 = nb2;
-    const double v = nv, dkl = ndkl;
-    if (t + 1 < ch.y) {
-      const int ti1 = ch.x + t + 1;
-      nbp2 = tiles[ti1].bp2;
-      nb2 = s.bp[nbp2];
-      nv = store[(long long)ti1 * kTile + tid];
-      ndkl = (kl < nb2.nI && ll < nb2.nJ) ? D[(nb2.sI + kl) * n + nb2.sJ + ll] : 0.0;
-    }
-    const bool dKL = b2.bI == b2.bJ;
-    const double wS = bp1 == bp2 ? 0.5 : 1.0;
+    const JkDesc b2 = desc[t];
+    const double v = v1, dkl = d1;
+    v1 = v2; d1 = d2;
+    if (t + 2 < ch.y) { v2 = store[(long long)(ch.x + t + 2) * kTile + tid]; d2 = load_dkl(t + 2); }
+    const bool dKL = b2.dKL != 0;
+    const double wS = b2.same_bp ? 0.5 : 1.0;
     jacc += (wS * (dKL ? 1.0 : 2.0)) * dkl * v;
     double* svb = sv + (t & 1) * (16 * 17);
     svb[bl * 17 + kt] = v;
     __syncthreads();
+    // digest by warps 0-1 only; the other warps run ahead into the next tile (double-buffered sv).  Measured: spreading
+    // the 1536 MACs over all 8 warps is slower (2.6 ms vs 2.2 ms per build) - the tile loop is bound by instruction issue
+    // and the stream of 2 KB tiles, not by the latency of these two warps.
     if (tid < 16) {                      // J[k,l] (lane = kl*4+ll)
       double acc = 0.0;
 #pragma unroll
       for (int q = 0; q < 16; ++q) acc += sdij[q] * svb[q * 17 + tid];
       const int k = tid >> 2, l = tid & 3;
-      if (k < b2.nI && l < b2.nJ && acc != 0.0) atomicAdd(Jacc + (b2.sI + k) * n + b2.sJ + l, wS * (dIJ ? 1.0 : 2.0) * acc);
+      if (k < b2.nK && l < b2.nL && acc != 0.0) atomicAdd(Jacc + (b2.sK + k) * n + b2.sL + l, wS * (dIJ ? 1.0 : 2.0) * acc);
     } else if (tid >= 32 && tid < 64) {  // K strips: thread (strip, r, x) owns K[strip row r, k = x] and K[strip row r, l = x]
       const int u = tid - 32, strip = u >> 4, r = (u >> 2) & 3, x = u & 3;
       const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
       // strip 0 (rows of I): K[i,k] += sum_{j,l} D[j,l] v[i j k l];  K[i,l] += sum_{j,k} D[j,k] v
       // strip 1 (rows of J): K[j,k] += sum_{i,l} D[i,l] v[i j k l];  K[j,l] += sum_{i,k} D[i,k] v
-      const double* dother = dstrip + (strip == 0 ? 4 : 0) * n;   // D rows of the OTHER bra block
+      const double* dother = dstrip + (strip == 0 ? 4 : 0) * ns;   // D rows of the OTHER bra block
       double a1 = 0.0, a2 = 0.0;
 #pragma unroll
       for (int o = 0; o < 4; ++o) {        // o: index inside the other bra block
         const int brow = strip == 0 ? (r * 4 + o) : (o * 4 + r);   // bra lane il*4+jl
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          a1 += dother[o * n + b2.sJ + y] * svb[brow * 17 + x * 4 + y];   // k = x, l = y
-          a2 += dother[o * n + b2.sI + y] * svb[brow * 17 + y * 4 + x];   // k = y, l = x
+          a1 += dother[o * ns + b2.sL + y] * svb[brow * 17 + x * 4 + y];   // k = x, l = y
+          a2 += dother[o * ns + b2.sK + y] * svb[brow * 17 + y * 4 + x];   // k = y, l = x
         }
       }
-      double* ks = kstrip + (strip * 4 + r) * n;
-      if (x < b2.nI) ks[b2.sI + x] += w * a1;
-      if (x < b2.nJ) ks[b2.sJ + x] += w * a2;
+      double* ks = kstrip + (strip * 4 + r) * ns;     // K == L: the same thread owns both updates, no race
+      if (x < b2.nK) ks[b2.sK + x] += w * a1;
+      if (x < b2.nL) ks[b2.sL + x] += w * a2;
     }
   }
   // J[i,j]: reduce the 16 ket lanes
@@ -339,10 +349,10 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
   for (int o = 8; o >= 1; o >>= 1) jacc += __shfl_xor_sync(0xffffffffu, jacc, o);
   if (kt == 0 && il < b1.nI && jl < b1.nJ && jacc != 0.0) atomicAdd(Jacc + (b1.sI + il) * n + b1.sJ + jl, jacc);
   __syncthreads();
-  for (int x = tid; x < 8 * n; x += 256) {
+  for (int x = tid; x < 8 * ns; x += 256) {
     const double val = kstrip[x];
     if (val != 0.0) {
-      const int row = x / n, col = x - row * n, r = row & 3;
+      const int row = x / ns, col = x - row * ns, r = row & 3;
       atomicAdd(Kacc + ((row >= 4 ? b1.sJ : b1.sI) + r) * n + col, val);
     }
   }
@@ -933,7 +943,7 @@ void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const Sys
 void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* store,
                       const double* D, double* Jacc, double* Kacc) {
   if (nchunks <= 0) return;
-  const size_t smem = ((size_t)16 * s.N + 2 * 16 * 17 + 16) * sizeof(double);
+  const size_t smem = ((size_t)16 * (s.N | 1) + 2 * 16 * 17 + 16) * sizeof(double) + 256 * 16;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(k_jk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
   k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
