@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kGradKetChunk = 9;   // ket primitive pairs whose adjoint slots are resident at once
+
 // ERI gradient: sum over the tile's quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
 //   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
 // where sum_terms <A, dG[B]> is the two-electron part of dE from the SCF reverse sweep.
@@ -377,10 +379,11 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
   const int KKb = c.b1.KK, KKk = c.b2.KK;
   double* sbra = sm;
   double* sket = sbra + KKb * kPairFields * 16;
-  double* sacc = sket + KKk * kPairFields * 16;     // [(KKk*5 + 2)][256]
-  const int nslots = KKk * kAdjFields + 2;
+  // ket adjoints accumulate in per-thread shared-memory slots; long contractions are walked in chunks of kGradKetChunk
+  // ket primitive pairs so that the slots stay within shared memory (STO-3G: 9 pairs = one chunk)
+  double* sacc = sket + KKk * kPairFields * 16;     // [(min(KKk, kGradKetChunk)*5 + 2)][256]
+  const int KC = KKk < kGradKetChunk ? KKk : kGradKetChunk;
   stage_pairs(c, pd, sbra, sket);
-  for (int x = 0; x < nslots; ++x) sacc[x * 256 + tid] = 0.0;
 
   double W = 0.0;
   if (c.valid) {
@@ -396,59 +399,69 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
     }
     W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (c.b1.bI == c.b1.bJ ? 0.5 : 1.0) * (c.b2.bI == c.b2.bJ ? 0.5 : 1.0);
   }
-  __syncthreads();
 
   const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
   const long long off5b = c.b1.off / kPairFields * kAdjFields, off5k = c.b2.off / kPairFields * kAdjFields;
   double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
-  for (int pb = 0; pb < KKb; ++pb) {
-    const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
-    PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
-    if (W != 0.0) {
-      for (int pk = 0; pk < KKk; ++pk) {
-        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
-        PairAdj ka; ka.P[0] = ka.P[1] = ka.P[2] = ka.g = ka.K = 0.0;
-        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-        prim_quartet<LA, LB, LC, LD, true>(bra, ket, ia, ib, ic, id, c_boys, W, &ba, &ka, &e0, &e1, &e2, &e3);
-        if (LA) { add3(ba.P, ia, e0); pas += e0; }
-        if (LB) { add3(ba.P, ib, e1); pbs += e1; }
-        if (LC) { add3(ka.P, ic, e2); qcs += e2; }
-        if (LD) { add3(ka.P, id, e3); qds += e3; }
-        double* a = sacc + (pk * kAdjFields) * 256 + tid;
-        a[0] += ka.P[0]; a[256] += ka.P[1]; a[512] += ka.P[2]; a[768] += ka.g; a[1024] += ka.K;
+  for (int k0 = 0; k0 < KKk; k0 += KC) {
+    const int kn = KKk - k0 < KC ? KKk - k0 : KC;
+    for (int x = 0; x < kn * kAdjFields; ++x) sacc[x * 256 + tid] = 0.0;
+    __syncthreads();      // (first chunk: also publishes the staged pair records)
+    for (int pb = 0; pb < KKb; ++pb) {
+      const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+      PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
+      if (W != 0.0) {
+        for (int pk = 0; pk < kn; ++pk) {
+          const PairPrim ket = load_pair(sket + (k0 + pk) * kPairFields * 16, c.kt);
+          PairAdj ka; ka.P[0] = ka.P[1] = ka.P[2] = ka.g = ka.K = 0.0;
+          double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+          prim_quartet<LA, LB, LC, LD, true>(bra, ket, ia, ib, ic, id, c_boys, W, &ba, &ka, &e0, &e1, &e2, &e3);
+          if (LA) { add3(ba.P, ia, e0); pas += e0; }
+          if (LB) { add3(ba.P, ib, e1); pbs += e1; }
+          if (LC) { add3(ka.P, ic, e2); qcs += e2; }
+          if (LD) { add3(ka.P, id, e3); qds += e3; }
+          double* a = sacc + (pk * kAdjFields) * 256 + tid;
+          a[0] += ka.P[0]; a[256] += ka.P[1]; a[512] += ka.P[2]; a[768] += ka.g; a[1024] += ka.K;
+        }
+      }
+      // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
+      double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
+#pragma unroll
+      for (int f = 0; f < kAdjFields; ++f) {
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) r[f] += __shfl_xor_sync(0xffffffffu, r[f], o);
+      }
+      if (c.kt == 0) {
+#pragma unroll
+        for (int f = 0; f < kAdjFields; ++f)
+          if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + c.bl, r[f]);
       }
     }
-    // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
-    double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
-#pragma unroll
-    for (int f = 0; f < kAdjFields; ++f) {
-#pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) r[f] += __shfl_xor_sync(0xffffffffu, r[f], o);
+    const bool last = k0 + kn >= KKk;
+    int nslots = kn * kAdjFields;
+    if (last) {           // the two contracted (Q-C), (Q-D) sums ride along with the last chunk
+      sacc[(nslots + 0) * 256 + tid] = qcs;
+      sacc[(nslots + 1) * 256 + tid] = qds;
+      nslots += 2;
     }
-    if (c.kt == 0) {
+    __syncthreads();
+    // ket adjoints: sum over the 16 bra lanes
+    for (int slot = tid >> 4; slot < nslots; slot += 16) {
+      double sum = 0.0;
 #pragma unroll
-      for (int f = 0; f < kAdjFields; ++f)
-        if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + c.bl, r[f]);
+      for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + c.kt];
+      if (sum != 0.0) {
+        if (slot < kn * kAdjFields) atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + slot) * 16 + c.kt, sum);
+        else atomicAdd(pasum + ((long long)tl.bp2 * 2 + (slot - kn * kAdjFields)) * 16 + c.kt, sum);
+      }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int o = 8; o >= 1; o >>= 1) { pas += __shfl_xor_sync(0xffffffffu, pas, o); pbs += __shfl_xor_sync(0xffffffffu, pbs, o); }
   if (c.kt == 0) {
     if (pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + c.bl, pas);
     if (pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + c.bl, pbs);
-  }
-  sacc[(KKk * kAdjFields + 0) * 256 + tid] = qcs;
-  sacc[(KKk * kAdjFields + 1) * 256 + tid] = qds;
-  __syncthreads();
-  // ket adjoints: sum over the 16 bra lanes
-  for (int slot = tid >> 4; slot < nslots; slot += 16) {
-    double sum = 0.0;
-#pragma unroll
-    for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + c.kt];
-    if (sum != 0.0) {
-      if (slot < KKk * kAdjFields) atomicAdd(padj + (off5k + slot) * 16 + c.kt, sum);
-      else atomicAdd(pasum + ((long long)tl.bp2 * 2 + (slot - KKk * kAdjFields)) * 16 + c.kt, sum);
-    }
   }
 }
 
@@ -927,13 +940,14 @@ void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const
 void launch_eri_grad_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
                            const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
   if (nt <= 0) return;
-  const size_t smem = ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kkmax * kAdjFields + 2) * 256) * sizeof(double);
+  const size_t smem = eri_grad_smem_bytes(kkmax);
 #define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, nt, s, pd, nterms, At, Bt, padj, pasum, smem)
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
 }
 size_t eri_grad_smem_bytes(int kkmax) {
-  return ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kkmax * kAdjFields + 2) * 256) * sizeof(double);
+  const int kc = kkmax < kGradKetChunk ? kkmax : kGradKetChunk;
+  return ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kc * kAdjFields + 2) * 256) * sizeof(double);
 }
 void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
                            double* packed) {

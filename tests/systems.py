@@ -45,3 +45,17 @@ FIXTURE_NAMES = ["h2", "h2o", "ch4", "hcn", "ch2o"]
 def ltype(l):
     """(lx,ly,lz) tuple -> 0 (s), 1 (px), 2 (py), 3 (pz)."""
     return 0 if max(l) == 0 else 1 + list(l).index(max(l))
+
+# systems without reference goldens (checked against the pinned CPU oracle only): long and mixed contractions
+from diffiqult_b200.Basis import basis_set_6G_STO_uncontracted as _u6  # noqa: E402
+
+_h6 = [p for _, prims in _u6[1] for p in prims]
+basis_h_6g = {1: [('S', [(e, c) for e, c in _h6])]}          # one s function contracted from 6 primitives (KK = 36)
+basis_mixed = {
+    1: [('S', basis_set_3G_STO[1][0][1][:2]), ('S', basis_set_3G_STO[1][0][1][2:])],        # 2 + 1 primitives
+    8: basis_set_3G_STO[8] + [('P', [(0.9, 1.0)]), ('S', [(0.35, 0.6), (1.7, 0.5), (9.0, 0.2), (40.0, 0.05)])],
+}
+EXTRA_SYSTEMS = {
+    "h2_6g": (syn.H2_EXAMPLE, basis_h_6g, 2),
+    "h2o_mixed": (syn.H2O, basis_mixed, 10),
+}

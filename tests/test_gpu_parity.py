@@ -330,3 +330,23 @@ def test_full_size_cluster_properties():
         fd = (e[0] - e[1]) / (2 * h)
         an = float(np.dot(r["grad"][n].ravel(), d.ravel()))
         assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (n, fd, an)
+
+
+@pytest.mark.parametrize("name", ["h2_6g", "h2o_mixed"])
+def test_long_and_mixed_contractions_vs_oracle(name):
+    """Contraction lengths 6 (36 primitive pairs: the gradient kernel walks the ket primitives in chunks) and a basis
+    mixing 1-, 2-, 3- and 4-primitive functions (function blocks split by contraction length)."""
+    mol, basis, ne = systems.EXTRA_SYSTEMS[name]
+    s = System_mol(mol, basis, ne, name)
+    a = orc.SysArrays(s)
+    cn = orc.normalization(a)
+    E = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    assert np.abs(E - orc.eri(a, cn)).max() < TOL_INT
+    r = Energy.rhf_grad(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100)
+    o = orc.rhf(a, max_scf=100)
+    assert r["status"] == o["status"] == 0 and r["niter"] == o["niter"]
+    assert abs(r["E"] - o["E"]) < TOL_E
+    for n in (0, 1, 2):
+        og = orc.rhf_grad(a, n, max_scf=100)
+        assert og["status"] == 0
+        assert np.abs(r["grad"][n] - og["grad"]).max() < TOL_G, (name, n)
