@@ -141,7 +141,7 @@ def run_ours(args):
     nq = prim_quartets(s)
     lnalpha = np.log(s.alpha)
     stream = distributed.current_stream_handle()
-    kw = dict(max_scf=100, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce)
+    kw = dict(max_scf=100, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce, jk_mode=args.jk_mode)
 
     def step():
         return Energy.rhf_grad(lnalpha, s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, **kw)
@@ -187,7 +187,8 @@ def run_ours(args):
             "config": {"workload": "(H2O)_%d STO-3G RHF energy + full parameter gradient (argnum 0,1,2)" % args.waters,
                        "n_basis": int(s.nbasis), "n_primitives": int(len(s.alpha)), "primitive_quartets": nq,
                        "scf_iterations": st["scf_iterations"], "converged": r["status"] == 0, "energy_hartree": r["E"],
-                       "jk_mode": "stored ERI tiles (%.2f GB per rank)" % (st["n_tiles"] * 2048 / 1e9),
+                       "jk_mode": ("integral-direct (tiles recomputed in every Fock build)" if st["jk_direct"] else
+                                   "stored ERI tiles (%.2f GB per rank)" % (st["n_tiles"] * 2048 / 1e9)),
                        "l2": "ERI tile store larger than L2; every step recomputes everything from host inputs",
                        "parallelism": "tiles round-robin over %d ranks; allreduce of J|K per Fock build and of the gradient" % world},
             "e2e": {"value": nq / (wall / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -220,6 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--waters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -113,6 +113,7 @@ struct TilePlan {
   std::vector<Tile> tiles;      // this rank's tiles, grouped by class
   std::vector<int2> chunks;     // runs of tiles sharing the bra block pair (J/K contraction)
   int cls_start[17];
+  int chunk_cls_start[17];      // chunk ranges per class
   long long n_quartets = 0, n_prim_quartets = 0;
   Tile* d_tiles = nullptr;
   int2* d_chunks = nullptr;
@@ -139,6 +140,8 @@ struct Prepared {
   const int* cls_start = nullptr;
   size_t ntiles = 0;
   double* d_store = nullptr;
+  bool direct = false;          // integral-direct Fock builds: tiles recomputed batch by batch into d_batch
+  double* d_batch = nullptr; size_t batch_tiles = 0;
   bool log_alpha = false;
   bool plan_only = false;       // host planning only (dq_plan): no CUDA call is made
   int world = 1, rank = 0;
@@ -293,13 +296,16 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
     for (int c = 0; c < 16; ++c) { tp->cls_start[c] = (int)tp->tiles.size(); tp->tiles.insert(tp->tiles.end(), by_cls[c].begin(), by_cls[c].end()); }
     tp->cls_start[16] = (int)tp->tiles.size();
     constexpr int kChunk = 256;
-    for (int c = 0; c < 16; ++c)
+    for (int c = 0; c < 16; ++c) {
+      tp->chunk_cls_start[c] = (int)tp->chunks.size();
       for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
         int e = t + 1;
         while (e < tp->cls_start[c + 1] && e - t < kChunk && tp->tiles[e].bp1 == tp->tiles[t].bp1) ++e;
         tp->chunks.push_back(make_int2(t, e - t));
         t = e;
       }
+    }
+    tp->chunk_cls_start[16] = (int)tp->chunks.size();
     if (!P.plan_only) {
       CU(cudaMalloc(&tp->d_tiles, std::max<size_t>(tp->tiles.size(), 1) * sizeof(Tile)));
       CU(cudaMalloc(&tp->d_chunks, std::max<size_t>(tp->chunks.size(), 1) * sizeof(int2)));
@@ -320,7 +326,28 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
+// decide stored vs integral-direct (dq_options.jk_mode) and allocate the tile store or the transient batch buffer
+static void setup_jk_mode(Prepared& P, const dq_options* opt) {
+  const int mode = opt ? opt->jk_mode : 0;
+  const size_t store_bytes = (size_t)P.ntiles * kTile * sizeof(double);
+  if (mode == 2) P.direct = true;
+  else if (mode == 1) P.direct = false;
+  else {
+    size_t fre = 0, tot = 0;
+    CU(cudaMemGetInfo(&fre, &tot));
+    P.direct = store_bytes > (fre + g_pool.cached_bytes) / 10 * 7;     // keep 30 % headroom for the SCF history
+  }
+  if (P.direct) {
+    size_t bytes = (opt && opt->direct_batch_bytes > 0) ? (size_t)opt->direct_batch_bytes : ((size_t)1 << 30);
+    P.batch_tiles = std::max<size_t>(bytes / (kTile * sizeof(double)), 256);   // at least one full chunk
+    P.batch_tiles = std::min(P.batch_tiles, std::max<size_t>(P.ntiles, 1));
+    P.d_batch = P.ws.alloc<double>(P.batch_tiles * kTile);
+  }
+  t_stats.jk_direct = P.direct ? 1 : 0;
+}
+
 static void compute_eri_store(Prepared& P) {
+  if (P.direct) return;
   P.d_store = P.ws.alloc<double>((size_t)P.ntiles * kTile);
   for (int c = 0; c < 16; ++c)
     launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
@@ -343,7 +370,25 @@ static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, do
   const int n = P.N;
   cudaStream_t st = P.ws.st;
   CU(cudaMemsetAsync(jk.JKacc, 0, sizeof(double) * 2 * n * n, st));
-  launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
+  if (!P.direct) {
+    launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
+  } else {
+    // integral-direct: for every class, runs of whole chunks that fit the batch buffer are evaluated and contracted at once
+    const TilePlan& tp = *P.tp;
+    for (int c = 0; c < 16; ++c) {
+      int c0 = tp.chunk_cls_start[c];
+      const int cend = tp.chunk_cls_start[c + 1];
+      while (c0 < cend) {
+        int c1 = c0; size_t nt = 0;
+        while (c1 < cend && nt + (size_t)tp.chunks[c1].y <= P.batch_tiles) { nt += tp.chunks[c1].y; ++c1; }
+        const int t0 = tp.chunks[c0].x;
+        launch_eri_tiles(st, c, P.d_tiles + t0, (int)nt, P.sd, P.d_pd, P.d_batch, P.kkmax);
+        launch_jk_chunks(st, P.d_tiles, P.d_chunks + c0, c1 - c0, P.sd, P.d_batch - (size_t)t0 * kTile, D, jk.JKacc,
+                         jk.JKacc + (size_t)n * n);
+        c0 = c1;
+      }
+    }
+  }
   if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, P.ar_user);
   launch_fock_combine(st, n, P.d_fblock, H, jk.JKacc, jk.JKacc + (size_t)n * n, F, G);
   t_stats.fock_builds++;
@@ -393,6 +438,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   t_stats.ms_one_electron = t_1e.stop();
 
   Timer t_eri(st);
+  setup_jk_mode(P, opt);
   compute_eri_store(P);                                                        // Energy.py:136
   t_stats.ms_eri = t_eri.stop();
 
@@ -648,6 +694,7 @@ int dq_fock(const dq_system* sys, const dq_options* opt, const double* D, double
   prepare(P, sys, opt, true, false);
   cudaStream_t st = P.ws.st;
   const int n = P.N; const size_t nn = (size_t)n * n;
+  setup_jk_mode(P, opt);
   compute_eri_store(P);
   double *S = P.ws.alloc<double>(nn), *T = P.ws.alloc<double>(nn), *V = P.ws.alloc<double>(nn), *H = P.ws.alloc<double>(nn);
   launch_one_electron(st, P.sd, S, T, V);

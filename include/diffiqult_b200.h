@@ -50,6 +50,9 @@ typedef struct dq_options {
   int32_t rank;            /* ... this process computes the tiles of `rank` */
   dq_allreduce_fn allreduce;   /* required when world_size > 1: sums partial J|K and gradient buffers */
   void* allreduce_user;
+  int32_t jk_mode;         /* Fock build (Energy.py:29-38): 0 auto, 1 stored ERI tiles (computed once, 8 B per contracted
+                            * quartet kept in HBM), 2 integral-direct (tiles recomputed batch by batch in every build) */
+  int64_t direct_batch_bytes;  /* integral-direct: size of the transient tile buffer (0: 1 GiB) */
 } dq_options;
 
 typedef struct dq_stats {
@@ -63,6 +66,7 @@ typedef struct dq_stats {
   int32_t scf_iterations;
   int32_t fock_builds;     /* J/K contractions (forward + reverse sweep) */
   int32_t grad_terms;      /* rank of the two-particle weight used by the ERI-gradient pass */
+  int32_t jk_direct;       /* 1 if the Fock builds were integral-direct, 0 if they used the stored tiles */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):
