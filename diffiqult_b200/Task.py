@@ -8,6 +8,8 @@ runs one full forward-mode SCF per entry of argnum: Task.py:44-51).
 Reference quirks, decided here:
   kept   : 99999 sentinel / status flag; kwargs such as printcoef/name are swallowed; gradient w.r.t. ln(alpha)
            (log=True) and w.r.t. the raw coefficients; results stored in sys.grad in argnum order.
+           'Opt' runs the reference's BFGS incl. its line-search quirk (Optimize.py / Linesearch.py restated in
+           diffiqult_b200/Optimize.py) so trajectories match the shipped examples.
   fixed  : gradient() evaluated everything twice (Task.py:412-413); _optupdateparam advanced the cursor by an array
            for argnum 1 (Task.py:308-310); _optimization returned an undefined `timer` when verbose=False
            (Task.py:346-352); Opt with argnum=[0,1,2] crashed in wrap_function (Optimize.py:281-287).
@@ -160,29 +162,18 @@ class Tasks(object):
 
     # ------------------------------------------------------------------ Opt (Task.py:281-392)
     def _BFGS(self, ene_function, grad_fun, args, argnums, log, name, **kwargs):
-        """BFGS over the selected argument groups (host loop; every f / gradient evaluation is one device call).
-        First cut on scipy.optimize.minimize: same objective, same gradients, same gtol rule (Task.py:288-291),
-        NOT the reference's modified line search, so trajectories differ from examples/*.out."""
-        from scipy.optimize import minimize
-        shapes = [np.shape(args[i]) for i in argnums]
-        sizes = [int(np.prod(s)) for s in shapes]
-        x0 = np.concatenate([np.asarray(args[i], dtype=np.float64).ravel() for i in argnums])
-        tol = 1e-05 if (log and 0 in argnums) else 1e-07
+        """Task.py:281-296: BFGS over the selected argument groups with the reference's optimiser (Optimize.py)."""
+        from .Minimize import minimize
+        print('Minimizing BFGS ...')
+        var = [args[i] for i in argnums]                 # arguments to optimise
+        rest = [a for i, a in enumerate(args) if i not in argnums]
+        tol = 1e-05 if (log and 0 in argnums) else 1e-07   # Task.py:288-291
+        dev = self.device
 
-        def split(x):
-            full, c = list(args), 0
-            for i, sh, sz in zip(argnums, shapes, sizes):
-                full[i] = x[c:c + sz].reshape(sh)
-                c += sz
-            return full
-
-        def f(x):
-            return ene_function(*split(x), device=self.device)
-
-        def g(x):
-            full = split(x)
-            return np.concatenate([np.ravel(gf(*full)) for gf in grad_fun])
-        return minimize(f, x0, jac=g, method='BFGS', options={'gtol': tol, 'maxiter': kwargs.get('maxiter', 30)})
+        def ene(*full):
+            return ene_function(*full, device=dev)
+        return minimize(ene, var, args=tuple(rest), argnum=list(argnums), method='BFGS', jac=grad_fun, gtol=tol, name=name,
+                        verbose=1 if self.verbose else 0, **kwargs)
 
     def _optupdateparam(self, argnum, x):
         c, nprim, nb = 0, len(self.sys.alpha), self.sys.nbasis
@@ -219,7 +210,7 @@ class Tasks(object):
 
     def optimization(self, max_scf=100, log=True, scf=True, name='Output', readguess=None, output=False, argnum=[0], **kwargs):
         name = self.name + '-task-' + str(self.ntask)
-        kwargs = {k: v for k, v in kwargs.items() if k in ('maxiter',)}
+        kwargs = {k: v for k, v in kwargs.items() if k in ('maxiter', 'reference_linesearch')}
         self._optimization(max_scf, log, scf, readguess, argnum, taskname=name, **kwargs)
 
     # ------------------------------------------------------------------ dispatch (Task.py:435-473)

@@ -372,3 +372,31 @@ def test_integral_direct_fock_build_matches_stored():
     F1, _ = Energy.fockmatrix(s.alpha, cn, s.xyz, s.l, s.charges, s.atom, s.list_contr, D, jk_mode="stored")
     F2, _ = Energy.fockmatrix(s.alpha, cn, s.xyz, s.l, s.charges, s.atom, s.list_contr, D, jk_mode="direct", direct_batch_bytes=1)
     assert np.abs(F1 - F2).max() < 1e-10 * max(1.0, np.abs(F1).max())
+
+
+def test_bfgs_reproduces_reference_examples():
+    """'Opt' end to end against the outputs the reference ships.
+    examples/h2o_optimization/h2_sto_3g.out:61-77 -- H2O/STO-3G, argnum=[0], maxiter=3: energy, gradient norm and the seven
+    printed exponents after 3 BFGS iterations (reproduced to every printed digit, incl. the reference's line-search quirk);
+    examples/h2_optimization/h2_sto_3g.out:28-38 -- H2/STO-3G, argnum=[0,1] to convergence: E = -1.095971."""
+    s = System_mol(synthetic.H2O, basis_set_3G_STO, 10, mol_name='agua')
+    m = Tasks(s, name='/tmp/dq_opt_h2o', verbose=False)
+    assert m.runtask('Energy', max_scf=50, printcoef=True, name='Output.molden', output=False)
+    m.runtask('Opt', max_scf=50, printcoef=False, maxiter=3, argnum=[0], output=False)
+    r = m.opt_result
+    assert r.nit == 3 and r.message == 'Maximum number of iterations has been exceeded.'
+    assert abs(r.fun - (-74.976643)) < 1e-6
+    assert abs(np.abs(r.jac).max() - 0.256754) < 1e-6
+    assert np.abs(s.alpha[:7] - [135.263104, 23.755473, 6.558207, 5.162051, 1.199706, 0.378480, 5.320693]).max() < 1e-6
+    s = System_mol(synthetic.H2_EXAMPLE, basis_set_3G_STO, 2, mol_name='agua')
+    m = Tasks(s, name='/tmp/dq_opt_h2', verbose=False)
+    assert m.runtask('Opt', max_scf=50, printcoef=False, argnum=[0, 1], output=True)
+    r = m.opt_result
+    assert r.status == 0 and abs(r.fun - (-1.095971)) < 1e-6 and np.abs(r.jac).max() < 1e-5
+    assert np.abs(s.alpha[:2] - [4.803590, 0.694786]).max() < 5e-4
+    # all three groups at once (crashes in the reference: Optimize.py:281-287)
+    s = System_mol(synthetic.H2_EXAMPLE, basis_set_3G_STO, 2)
+    m = Tasks(s, name='/tmp/dq_opt_h2_012', verbose=False)
+    e0 = Energy.rhf(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=50)["E"]
+    m.runtask('Opt', max_scf=50, argnum=[0, 1, 2], maxiter=4, reference_linesearch=False)
+    assert m.opt_result.fun < e0 - 1e-3
