@@ -113,7 +113,7 @@ def run_reference(args):
                   "(the reference's algorithm, Task.py:25-51), C++/OpenMP port oracle/rhf_oracle.cpp; the reference itself is "
                   "single-threaded Python 2 + algopy and cannot run (H2O)_%d at all" % (sample, args.waters))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "(H2O)_%d STO-3G RHF energy + full parameter gradient (argnum 0,1,2)" % args.waters,
                        "n_basis": int(s_full.nbasis), "n_primitives": int(len(s_full.alpha)),

@@ -1,9 +1,3 @@
-"""minimize(): the dispatcher of the reference (diffiqult/Minimize.py:10-16)."""
-from .Optimize import minimize_bfgs
-
-
-def minimize(fun, x0, args=(), method='BFGS', jac=None, tol=None, gtol=None, callback=None, argnum=None, name=None,
-             **options):
-    if method == 'BFGS':
-        return minimize_bfgs(fun, x0, args, argnum, jac, callback, name, gtol, **options)
-    raise ValueError('Unknown solver %s' % method)
+"""Import-compatibility shim: the reference keeps its solver dispatcher in a module of this name
+(diffiqult/Minimize.py); here it lives next to the solver in Optimize.py."""
+from .Optimize import minimize  # noqa: F401

@@ -196,3 +196,15 @@ def minimize_bfgs(fun, x0, args=(), argnum=None, jac=None, callback=None, name=N
     if return_all:
         result['allvecs'] = allvecs
     return result
+
+
+_SOLVERS = {'BFGS': minimize_bfgs}
+
+
+def minimize(fun, x0, args=(), method='BFGS', jac=None, tol=None, gtol=None, callback=None, argnum=None, name=None,
+             **options):
+    """Solver dispatch with the call signature of the reference's Minimize.minimize (Minimize.py:10-16); BFGS only."""
+    solver = _SOLVERS.get(method)
+    if solver is None:
+        raise ValueError('Unknown solver %s' % method)
+    return solver(fun, x0, args=args, argnum=argnum, jac=jac, callback=callback, name=name, gtol=gtol, **options)

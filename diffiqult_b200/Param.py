@@ -1,5 +1,7 @@
-"""Element look-ups used by the text writers (reference: diffiqult/Param.py:1-16)."""
+"""Element look-ups used by the text writers (same names as the reference's diffiqult/Param.py)."""
 
-select_atom = {1: "H", 3: "Li", 6: "C", 7: "N", 8: "O", 9: "F"}
+# Z, symbol, mass used by the reference (None: the reference has no entry)
+_ELEMENTS = ((1, "H", 1.00794), (3, "Li", None), (6, "C", 12), (7, "N", 15), (8, "O", 16), (9, "F", 18.998403))
 
-select_weight = {1: 1.00794, 6: 12, 7: 15, 8: 16, 9: 18.998403}
+select_atom = {z: sym for z, sym, _ in _ELEMENTS}
+select_weight = {z: w for z, _, w in _ELEMENTS if w is not None}

@@ -170,8 +170,6 @@ static void check_system(const dq_system* s) {
 static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool need_tiles, bool normalise) {
   check_system(s);
   int dev = opt ? opt->device : 0;
-  int ndev = 0;
-  (void)ndev;
   if (!P.plan_only) need_device(dev);
   P.ws.dev = dev;
   P.ws.st = opt ? (cudaStream_t)opt->stream : 0;
