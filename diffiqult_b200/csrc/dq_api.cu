@@ -435,21 +435,10 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   launch_axpby(st, (int)nn, 1.0, V, 1.0, H);                                  // Energy.py:137
   t_stats.ms_one_electron = t_1e.stop();
 
-  Timer t_eri(st);
-  setup_jk_mode(P, opt);
-  compute_eri_store(P);                                                        // Energy.py:136
-  t_stats.ms_eri = t_eri.stop();
-
-  Timer t_scf(st);
-  // S^-1/2 = L diag(w^-1/2) L^T                                               // Energy.py:138-144
+  // SCF buffers
   double *L = ws.alloc<double>(nn), *wS = ws.alloc<double>(n), *X = ws.alloc<double>(nn), *t1 = ws.alloc<double>(nn),
          *t2 = ws.alloc<double>(nn), *t3 = ws.alloc<double>(nn), *vwork = ws.alloc<double>(nn);
   void* ework = ws.alloc<char>(eigh_workspace_bytes(n, 1));
-  CU(cudaMemcpyAsync(t1, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  launch_eigh(st, n, 1, t1, vwork, L, wS, ework);
-  launch_scale_cols_rsqrt(st, n, L, wS, t2);
-  launch_gemm(st, false, true, n, n, n, t2, n, L, n, X, n, 1.0, 0.0);
-
   JK jk; jk.JKacc = ws.alloc<double>(2 * nn);
   double *F = ws.alloc<double>(nn), *Fp = ws.alloc<double>(nn), *U = ws.alloc<double>(nn), *C = ws.alloc<double>(nn),
          *D = ws.alloc<double>(nn), *eps = ws.alloc<double>(n), *dE = ws.alloc<double>(1);
@@ -457,7 +446,62 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   std::vector<double*> hFprev, hU, hEps, hD, hF;
   double* slab = nullptr; int slab_left = 0;
   auto hist = [&](size_t cnt) { double* p = slab; slab += cnt; return p; };
-  CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));          // Energy.py:159 (core guess)
+
+  // everything of an SCF iteration that precedes the Fock build: F' = X^T F X, eigensolve, C = X U, D = C_occ C_occ^T
+  auto scf_pre = [&](int it, cudaStream_t sx) {
+    if (want_grad) {
+      if (slab_left == 0) { slab = ws.alloc<double>((size_t)16 * (4 * nn + n)); slab_left = 16; }
+      --slab_left;
+      double* f = hist(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, sx)); hFprev.push_back(f);
+    }
+    launch_gemm(sx, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
+    launch_gemm(sx, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
+    // Energy.py:167-168.  Warm start: successive Fock matrices are close, so F' is first rotated into the previous
+    // iteration's eigenbasis (nearly diagonal -> Jacobi converges in 2-4 sweeps instead of ~9); U = U_prev V.
+    if (it == 0 || getenv("DQ_COLD_EIGH")) {
+      launch_eigh(sx, n, 1, Fp, vwork, U, eps, ework);
+    } else {
+      launch_gemm(sx, true, false, n, n, n, U, n, Fp, n, t1, n, 1.0, 0.0);      // U_prev^T F'
+      launch_gemm(sx, false, false, n, n, n, t1, n, U, n, t2, n, 1.0, 0.0);     // U_prev^T F' U_prev
+      launch_symmetrize(sx, n, t2);
+      launch_eigh(sx, n, 1, t2, vwork, t3, eps, ework);
+      launch_gemm(sx, false, false, n, n, n, U, n, t3, n, t1, n, 1.0, 0.0);     // U_prev V
+      CU(cudaMemcpyAsync(U, t1, nn * sizeof(double), cudaMemcpyDeviceToDevice, sx));
+    }
+    launch_gemm(sx, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
+    launch_gemm(sx, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180
+  };
+
+  // S^-1/2 and the whole first iteration up to its Fock build depend only on S and H: they run on a side stream,
+  // concurrently with the ERI pass (single-CTA eigensolver kernels next to 1.27 M tile CTAs).
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_1e = nullptr, ev_side = nullptr;
+  {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&ev_1e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+  }
+  struct SideGuard { cudaStream_t s; cudaEvent_t a, b; ~SideGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); cudaEventDestroy(a); cudaEventDestroy(b); } } side_guard{side, ev_1e, ev_side};
+  CU(cudaEventRecord(ev_1e, st));
+  CU(cudaStreamWaitEvent(side, ev_1e, 0));
+  // S^-1/2 = L diag(w^-1/2) L^T                                               // Energy.py:138-144
+  CU(cudaMemcpyAsync(t1, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, side));
+  launch_eigh(side, n, 1, t1, vwork, L, wS, ework);
+  launch_scale_cols_rsqrt(side, n, L, wS, t2);
+  launch_gemm(side, false, true, n, n, n, t2, n, L, n, X, n, 1.0, 0.0);
+  CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, side));        // Energy.py:159 (core guess)
+  scf_pre(0, side);
+  CU(cudaEventRecord(ev_side, side));
+
+  Timer t_eri(st);
+  setup_jk_mode(P, opt);
+  compute_eri_store(P);                                                        // Energy.py:136
+  t_stats.ms_eri = t_eri.stop();
+
+  Timer t_scf(st);
+  CU(cudaStreamWaitEvent(st, ev_side, 0));
   double oldE = 1e8, e_elec = 0.0;
   out.esteps.clear();
   out.converged = false;
@@ -465,30 +509,9 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   for (int it = 0; it < max_scf; ++it) {
     double tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
     auto now = [&]() { cudaStreamSynchronize(st); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
-    if (trace) tr0 = now();
-    if (want_grad) {
-      if (slab_left == 0) { slab = ws.alloc<double>((size_t)16 * (4 * nn + n)); slab_left = 16; }
-      --slab_left;
-      double* f = hist(nn); CU(cudaMemcpyAsync(f, F, nn * sizeof(double), cudaMemcpyDeviceToDevice, st)); hFprev.push_back(f);
-    }
-    launch_gemm(st, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
-    launch_gemm(st, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
-    if (trace) tr1 = now();
-    // Energy.py:167-168.  Warm start: successive Fock matrices are close, so F' is first rotated into the previous
-    // iteration's eigenbasis (nearly diagonal -> Jacobi converges in 2-4 sweeps instead of ~9); U = U_prev V.
-    if (it == 0 || getenv("DQ_COLD_EIGH")) {
-      launch_eigh(st, n, 1, Fp, vwork, U, eps, ework);
-    } else {
-      launch_gemm(st, true, false, n, n, n, U, n, Fp, n, t1, n, 1.0, 0.0);      // U_prev^T F'
-      launch_gemm(st, false, false, n, n, n, t1, n, U, n, t2, n, 1.0, 0.0);     // U_prev^T F' U_prev
-      launch_symmetrize(st, n, t2);
-      launch_eigh(st, n, 1, t2, vwork, t3, eps, ework);
-      launch_gemm(st, false, false, n, n, n, U, n, t3, n, t1, n, 1.0, 0.0);     // U_prev V
-      CU(cudaMemcpyAsync(U, t1, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    }
+    if (trace) tr0 = tr1 = now();
+    if (it > 0) scf_pre(it, st);
     if (trace) tr2 = now();
-    launch_gemm(st, false, false, n, n, n, X, n, U, n, C, n, 1.0, 0.0);       // Energy.py:169
-    launch_gemm(st, false, true, n, n, ne, C, n, C, n, D, n, 1.0, 0.0);       // Energy.py:174-180
     fock_build(P, jk, D, H, F, nullptr);                                       // Energy.py:188
     launch_dot3(st, (int)nn, D, H, F, dE);                                     // Energy.py:189
     CU(cudaMemcpyAsync(&e_elec, dE, sizeof(double), cudaMemcpyDeviceToHost, st));
