@@ -141,7 +141,8 @@ def run_ours(args):
     nq = prim_quartets(s)
     lnalpha = np.log(s.alpha)
     stream = distributed.current_stream_handle()
-    kw = dict(max_scf=100, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce, jk_mode=args.jk_mode)
+    kw = dict(max_scf=100, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce, jk_mode=args.jk_mode,
+              screen_threshold=args.screen)
 
     def step():
         return Energy.rhf_grad(lnalpha, s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, **kw)
@@ -190,6 +191,8 @@ def run_ours(args):
                        "jk_mode": ("integral-direct (tiles recomputed in every Fock build)" if st["jk_direct"] else
                                    "stored ERI tiles (%.2f GB per rank)" % (st["n_tiles"] * 2048 / 1e9)),
                        "l2": "ERI tile store larger than L2; every step recomputes everything from host inputs",
+                       "screening": ("off: all %d primitive quartets evaluated, as in the reference" % nq) if args.screen <= 0 else
+                                    ("opt-in threshold %g: %d of %d tiles skipped" % (args.screen, st["n_tiles_skipped"], st["n_tiles"])),
                        "parallelism": "tiles round-robin over %d ranks; allreduce of J|K per Fock build and of the gradient" % world},
             "e2e": {"value": nq / (wall / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(np.sum([x["launches"] for x in stats])),
@@ -222,6 +225,7 @@ def main():
     ap.add_argument("--waters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])
+    ap.add_argument("--screen", type=float, default=0.0, help="opt-in tile screening threshold (default 0: evaluate everything, as the reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,7 +24,8 @@ class dq_system(C.Structure):
 class dq_options(C.Structure):
     _fields_ = [("max_scf", C.c_int32), ("e_tol", C.c_double), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("world_size", C.c_int32), ("rank", C.c_int32), ("allreduce", ALLREDUCE_FN),
-                ("allreduce_user", C.c_void_p), ("jk_mode", C.c_int32), ("direct_batch_bytes", C.c_int64)]
+                ("allreduce_user", C.c_void_p), ("jk_mode", C.c_int32), ("direct_batch_bytes", C.c_int64),
+                ("screen_threshold", C.c_double)]
 
 
 class dq_stats(C.Structure):
@@ -32,7 +33,7 @@ class dq_stats(C.Structure):
                 ("ms_scf", C.c_double), ("ms_reverse", C.c_double), ("ms_eri_grad", C.c_double),
                 ("ms_grad_other", C.c_double), ("ms_total", C.c_double), ("launches", C.c_int64), ("n_tiles", C.c_int64),
                 ("n_quartets", C.c_int64), ("n_prim_quartets", C.c_int64), ("scf_iterations", C.c_int32),
-                ("fock_builds", C.c_int32), ("grad_terms", C.c_int32), ("jk_direct", C.c_int32)]
+                ("fock_builds", C.c_int32), ("grad_terms", C.c_int32), ("jk_direct", C.c_int32), ("n_tiles_skipped", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -127,7 +128,8 @@ JK_MODES = {"auto": 0, "stored": 1, "direct": 2}
 
 
 def options(max_scf=30, e_tol=0.0, device=0, stream=None, world_size=1, rank=0, allreduce=None, jk_mode="auto",
-            direct_batch_bytes=0):
+            direct_batch_bytes=0, screen_threshold=0.0):
     return dq_options(int(max_scf), float(e_tol), int(device), C.c_void_p(stream) if stream else None, int(world_size),
                       int(rank), allreduce if allreduce is not None else _noop_allreduce, None,
-                      JK_MODES[jk_mode] if isinstance(jk_mode, str) else int(jk_mode), int(direct_batch_bytes))
+                      JK_MODES[jk_mode] if isinstance(jk_mode, str) else int(jk_mode), int(direct_batch_bytes),
+                      float(screen_threshold))

@@ -140,6 +140,7 @@ struct Prepared {
   const int* cls_start = nullptr;
   size_t ntiles = 0;
   double* d_store = nullptr;
+  unsigned long long* d_skipped = nullptr;
   bool direct = false;          // integral-direct Fock builds: tiles recomputed batch by batch into d_batch
   double* d_batch = nullptr; size_t batch_tiles = 0;
   bool log_alpha = false;
@@ -266,6 +267,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
   sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
+  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr;
   }
 
   if (!need_tiles) return;
@@ -320,7 +322,12 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   P.d_tiles = tp->d_tiles; P.d_chunks = tp->d_chunks; P.nchunks = (int)tp->chunks.size();
   if (((size_t)16 * N + 2 * 16 * 17 + 16) * sizeof(double) > 220 * 1024) fail(-1, "basis too large for the J/K kernel's shared-memory row strips");
   P.d_pd = ws.alloc<double>(P.pd_len);
-  launch_pairs(st, P.sd, P.d_pd);
+  double* d_kmax = ws.alloc<double>(P.nbp);
+  P.d_skipped = ws.alloc<unsigned long long>(1, true);
+  P.sd.bp_kmax = d_kmax;
+  P.sd.screen = (opt && opt->screen_threshold > 0.0) ? opt->screen_threshold : 0.0;
+  P.sd.skipped = P.d_skipped;
+  launch_pairs(st, P.sd, P.d_pd, d_kmax);
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
@@ -618,6 +625,12 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     if (g_xyz) for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) g_xyz[3 * P.f_orig[i] + c] = hx[3 * i + c];
     t_stats.ms_grad_other = t_g.stop() - t_stats.ms_eri_grad;
     t_stats.grad_terms = nterms;
+  }
+  if (P.sd.screen > 0.0 && !P.direct) {
+    unsigned long long sk = 0;
+    CU(cudaMemcpyAsync(&sk, P.d_skipped, sizeof sk, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t_stats.n_tiles_skipped = (int64_t)sk;
   }
   CU(cudaStreamSynchronize(st));
   t_stats.ms_total = t_total.stop();

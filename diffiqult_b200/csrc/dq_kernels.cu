@@ -98,8 +98,9 @@ __global__ void k_normalize_bwd(int N, const int* __restrict__ f_off, const int*
 // =============================================================================================
 // primitive-pair records
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_pairs(SystemDev s, double* __restrict__ pd) {
+__global__ void __launch_bounds__(128) k_pairs(SystemDev s, double* __restrict__ pd, double* __restrict__ bp_kmax) {
   const BlockPair b = s.bp[blockIdx.x];
+  double kmax = 0.0;
   const int lane = threadIdx.x & 15, il = lane >> 2, jl = lane & 3;
   const bool valid = il < b.nI && jl < b.nJ;
   const int i = b.sI + il, j = b.sJ + jl;
@@ -114,7 +115,10 @@ __global__ void __launch_bounds__(128) k_pairs(SystemDev s, double* __restrict__
     }
     double* o = pd + ((b.off + (long long)pp * kPairFields) * 16 + lane);
     o[0] = r.P[0]; o[16] = r.P[1]; o[32] = r.P[2]; o[48] = r.g; o[64] = r.ginv; o[80] = r.K; o[96] = r.pa; o[112] = r.pb;
+    kmax = fmax(kmax, fabs(r.K));
   }
+  // non-negative doubles order like their bit patterns (bp_kmax is zeroed by the launcher)
+  if (kmax > 0.0) atomicMax((unsigned long long*)(bp_kmax + blockIdx.x), (unsigned long long)__double_as_longlong(kmax));
 }
 
 __device__ __forceinline__ PairPrim load_pair(const double* __restrict__ rec, int lane) {
@@ -209,10 +213,21 @@ __device__ __forceinline__ void stage_pairs(const TileCtx& c, const double* __re
   for (int x = threadIdx.x; x < nk; x += blockDim.x) sket[x] = gk[x];
 }
 
+// opt-in screening (dq_options.screen_threshold): 2 pi^(5/2) max|K_ab| max|K_cd| bounds the prefactor of every primitive
+// quartet of the tile; CTA-uniform
+__device__ __forceinline__ bool tile_screened(const SystemDev& s, const Tile tl) {
+  return s.screen > 0.0 && kTwoPi52 * s.bp_kmax[tl.bp1] * s.bp_kmax[tl.bp2] < s.screen;
+}
+
 template <bool LA, bool LB, bool LC, bool LD>
 __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd,
                                                    double* __restrict__ store) {
   extern __shared__ double sm[];
+  if (tile_screened(s, tiles[blockIdx.x])) {
+    store[(long long)blockIdx.x * kTile + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) atomicAdd(s.skipped, 1ULL);
+    return;
+  }
   const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
   double* sbra = sm;
   double* sket = sm + c.b1.KK * kPairFields * 16;
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__
 //   K[i,k], K[j,k], K[i,l], K[j,l]    accumulated in two shared-memory row strips K[I,:], K[J,:], flushed once
 // with D[I,:], D[J,:] staged in shared memory.  Diagonal tiles carry weights 1/2 so that every tile is treated
 // uniformly (final J: upper block triangle mirrored; final K = Kacc + Kacc^T; DESIGN.md "Fock build").
-struct JkDesc { int sK, sL; short nK, nL; short same_bp, dKL; };   // ket block pair of one tile, 16 bytes
+struct JkDesc { int sK, sL; short nK, nL; unsigned char same_bp, dKL, skip, pad_; };   // ket block pair of one tile, 16 bytes
 
 __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
                                                    const double* __restrict__ store, const double* __restrict__ D,
@@ -283,6 +298,7 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
     const int bp2 = tiles[ch.x + tid].bp2;
     const BlockPair b2 = s.bp[bp2];
     JkDesc d; d.sK = b2.sI; d.sL = b2.sJ; d.nK = (short)b2.nI; d.nL = (short)b2.nJ; d.same_bp = bp2 == bp1; d.dKL = b2.bI == b2.bJ;
+    d.skip = tile_screened(s, tiles[ch.x + tid]); d.pad_ = 0;
     desc[tid] = d;
   }
   for (int x = tid; x < 8 * ns; x += 256) {
@@ -299,19 +315,23 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
   // software pipeline, depth 2: ERI value and D_kl of tiles t+1, t+2 are in flight while tile t is digested
   auto load_dkl = [&](int t) {
     const JkDesc d = desc[t];
-    return (kl < d.nK && ll < d.nL) ? D[(d.sK + kl) * n + d.sL + ll] : 0.0;
+    return (!d.skip && kl < d.nK && ll < d.nL) ? D[(d.sK + kl) * n + d.sL + ll] : 0.0;
   };
-  double v1 = store[(long long)ch.x * kTile + tid], d1 = load_dkl(0), v2 = 0.0, d2 = 0.0;
-  if (ch.y > 1) { v2 = store[(long long)(ch.x + 1) * kTile + tid]; d2 = load_dkl(1); }
+  auto load_v = [&](int t) { return desc[t].skip ? 0.0 : store[(long long)(ch.x + t) * kTile + tid]; };   // screened tiles are not read
+  double v1 = load_v(0), d1 = load_dkl(0), v2 = 0.0, d2 = 0.0;
+  if (ch.y > 1) { v2 = load_v(1); d2 = load_dkl(1); }
+  int nproc = 0;                        // processed (non-screened) tiles: selects the sv buffer
   for (int t = 0; t < ch.y; ++t) {
     const JkDesc b2 = desc[t];
     const double v = v1, dkl = d1;
     v1 = v2; d1 = d2;
-    if (t + 2 < ch.y) { v2 = store[(long long)(ch.x + t + 2) * kTile + tid]; d2 = load_dkl(t + 2); }
+    if (t + 2 < ch.y) { v2 = load_v(t + 2); d2 = load_dkl(t + 2); }
+    if (b2.skip) continue;
     const bool dKL = b2.dKL != 0;
     const double wS = b2.same_bp ? 0.5 : 1.0;
     jacc += (wS * (dKL ? 1.0 : 2.0)) * dkl * v;
-    double* svb = sv + (t & 1) * (16 * 17);
+    double* svb = sv + (nproc & 1) * (16 * 17);
+    ++nproc;
     svb[bl * 17 + kt] = v;
     __syncthreads();
     // digest by warps 0-1 only; the other warps run ahead into the next tile (double-buffered sv).  Measured: spreading
@@ -374,6 +394,7 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
                  double* __restrict__ pasum) {
   extern __shared__ double sm[];
   const Tile tl = tiles[blockIdx.x];
+  if (tile_screened(s, tl)) return;
   const TileCtx c = tile_ctx(tl, s);
   const int tid = threadIdx.x;
   const int KKb = c.b1.KK, KKk = c.b2.KK;
@@ -883,8 +904,9 @@ void launch_normalize_bwd(cudaStream_t st, int N, const int* f_off, const int* f
                           const double* cbar, double* abar, double* crawbar) {
   k_normalize_bwd<<<cdiv(N, 128), 128, 0, st>>>(N, f_off, f_type, alpha, craw, cbar, abar, crawbar); DQ_LAUNCHED();
 }
-void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd) {
-  k_pairs<<<s.nbp, 128, 0, st>>>(s, pd); DQ_LAUNCHED();
+void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd, double* bp_kmax) {
+  cudaMemsetAsync(bp_kmax, 0, sizeof(double) * s.nbp, st);
+  k_pairs<<<s.nbp, 128, 0, st>>>(s, pd, bp_kmax); DQ_LAUNCHED();
 }
 void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V) {
   k_one_electron<<<cdiv((long long)s.N * (s.N + 1) / 2, 64), 64, 0, st>>>(s, S, T, V); DQ_LAUNCHED();

@@ -14,7 +14,7 @@ void reset_launch_count();
 void launch_normalize(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw, double* cn);
 void launch_normalize_bwd(cudaStream_t st, int N, const int* f_off, const int* f_type, const double* alpha, const double* craw,
                           const double* cbar, double* abar, double* crawbar);
-void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd);
+void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd, double* bp_kmax);
 void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V);
 void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar, double* g_alpha,
                               double* g_coef, double* g_xyz);

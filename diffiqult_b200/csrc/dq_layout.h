@@ -42,6 +42,9 @@ struct SystemDev {
   const int* Z;            // [natoms]
   const double* C;         // [natoms][3]
   const BlockPair* bp;     // [nbp]
+  const double* bp_kmax;   // [nbp]  max |K_ab| over the primitive-pair records of each block pair
+  double screen;           // opt-in tile screening threshold (0: off)
+  unsigned long long* skipped;   // counter of skipped tiles (screening on)
 };
 
 }  // namespace dq

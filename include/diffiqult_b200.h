@@ -53,6 +53,9 @@ typedef struct dq_options {
   int32_t jk_mode;         /* Fock build (Energy.py:29-38): 0 auto, 1 stored ERI tiles (computed once, 8 B per contracted
                             * quartet kept in HBM), 2 integral-direct (tiles recomputed batch by batch in every build) */
   int64_t direct_batch_bytes;  /* integral-direct: size of the transient tile buffer (0: 1 GiB) */
+  double screen_threshold; /* 0 (default): every quartet is evaluated, as in the reference, which screens nothing.
+                            * > 0 (opt-in): a tile is skipped when 2 pi^(5/2) max|K_ab| max|K_cd| over its two block
+                            * pairs is below the threshold (an upper bound of its primitive prefactors) */
 } dq_options;
 
 typedef struct dq_stats {
@@ -67,6 +70,7 @@ typedef struct dq_stats {
   int32_t fock_builds;     /* J/K contractions (forward + reverse sweep) */
   int32_t grad_terms;      /* rank of the two-particle weight used by the ERI-gradient pass */
   int32_t jk_direct;       /* 1 if the Fock builds were integral-direct, 0 if they used the stored tiles */
+  int64_t n_tiles_skipped; /* tiles skipped by the opt-in screening in the (last) ERI pass */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):

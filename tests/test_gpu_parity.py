@@ -400,3 +400,17 @@ def test_bfgs_reproduces_reference_examples():
     e0 = Energy.rhf(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=50)["E"]
     m.runtask('Opt', max_scf=50, argnum=[0, 1, 2], maxiter=4, reference_linesearch=False)
     assert m.opt_result.fun < e0 - 1e-3
+
+
+def test_optin_screening_keeps_results_within_tolerance():
+    """screen_threshold is off by default (the reference screens nothing).  Opt-in: tiles whose primitive prefactors are
+    bounded below the threshold are skipped; energy and gradient stay within the parity tolerances."""
+    mol = synthetic.water_cluster(8)
+    s = System_mol(mol, basis_set_3G_STO, 80, "w8")
+    args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+    a = Energy.rhf_grad(*args, max_scf=100)
+    b = Energy.rhf_grad(*args, max_scf=100, screen_threshold=1e-18)
+    assert a["stats"]["n_tiles_skipped"] == 0 and b["stats"]["n_tiles_skipped"] > a["stats"]["n_tiles"] // 2
+    assert a["niter"] == b["niter"] and abs(a["E"] - b["E"]) < 1e-10
+    for n in range(3):
+        assert np.abs(a["grad"][n] - b["grad"][n]).max() < 1e-8
