@@ -72,4 +72,10 @@ def rhfenergy(alpha_old, coef2, xyz, l, charges, xyz_atom, natoms, nbasis, contr
         print('E_tot: ' + str(r["E"]) + '\n')
         print('SCF DID NOT CONVERGED')
         return SCF_FAILED
+    if write:   # Energy.py:311-316: name.molden is written only for a converged SCF
+        from . import Integrals, Molden
+        alpha = np.exp(np.asarray(alpha_old, dtype=np.float64)) if log else np.asarray(alpha_old, dtype=np.float64)
+        coefn = Integrals.normalization(alpha, coef2, l, contr_list, device=device)
+        Molden.write_molden(str(name) + '.molden', r, alpha, coefn, np.asarray(xyz, dtype=np.float64), l, charges,
+                            np.asarray(xyz_atom, dtype=np.float64), contr_list, ne, device=device)
     return r["E"]

@@ -414,3 +414,30 @@ def test_optin_screening_keeps_results_within_tolerance():
     assert a["niter"] == b["niter"] and abs(a["E"] - b["E"]) < 1e-10
     for n in range(3):
         assert np.abs(a["grad"][n] - b["grad"][n]).max() < 1e-8
+
+
+def test_molden_output_diffs_against_the_reference_file(golden, tmp_path):
+    """Tasks.runtask('Energy', output=True) writes name-<ntask>.molden in the reference's layout; parsed with the parser
+    that packed tests/output.molden (the reference's recorded CH4 run) it carries the same numbers."""
+    g = golden["molden_ch4"]
+    s = sysmol("ch4")
+    m = Tasks(s, name=str(tmp_path / "ch4"), verbose=False)
+    assert m.runtask('Energy', max_scf=100, output=True)
+    lines = open(str(tmp_path / "ch4-1.molden")).read().split("\n")
+    assert lines[0] == '[Energy] ' and lines[4] == 'SCF Details' and lines[5] == 'Eigen: True'
+    assert abs(float(lines[1].split()[1]) - float(g["E_elec"])) < 2e-10
+    assert abs(float(lines[2].split()[1]) - float(g["E_nuc"])) < 2e-9
+    assert abs(float(lines[3].split()[1]) - float(g["E_tot"])) < 2e-10
+    steps = [float(x.split()[2]) for x in lines if x.startswith("Step:")]
+    assert len(steps) == 12 and np.abs(np.array(steps) - g["steps"]).max() < 2e-10
+    for tag in ("[CM] ", "[DM] ", "[NMO] ", "[MOE] ", "[INPUT] ", "[Atoms]", "[GTO]", "[MO]"):
+        assert tag in lines
+    i = lines.index("[DM] ")
+    D = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[i + 3:i + 3 + 18]])
+    assert np.abs(D - g["D"]).max() < 1e-8
+    i = lines.index("[MOE] ")
+    moe = np.array([float(ln.split()[1]) for ln in lines[i + 2:i + 20]])
+    assert np.abs(moe - g["moe"]).max() < 1e-9
+    i = lines.index("[GTO]")
+    gto = [tuple(float(x) for x in ln.split()) for ln in lines[i + 1:lines.index("[MO]")] if len(ln.split()) == 2 and "." in ln.split()[0]]
+    assert np.abs(np.array(gto) - g["gto"]).max() < 1e-11
