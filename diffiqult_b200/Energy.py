@@ -28,28 +28,30 @@ def fockmatrix(alpha, coef, xyz, l, charges, atoms, contr_list, D, device=0, jk_
 
 
 def rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
-        world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0):
+        world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None):
     """Full result of one RHF single point: dict(E, status, niter, esteps, C, eps, stats)."""
     a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
     n = a.nbasis
     E, nit = C.c_double(0.0), C.c_int32(0)
     es, Cm, eps = np.zeros(max(int(max_scf), 1)), np.zeros((n, n)), np.zeros(n)
+    guess = None if guess_C is None else np.ascontiguousarray(guess_C, dtype=np.float64)
     opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce,
-                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold)
+                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess)
     st = _capi.check(_capi.lib().dq_rhf(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), es.ctypes, Cm.ctypes,
                                         eps.ctypes), allow=(0, 1))
     return dict(E=E.value, status=st, niter=nit.value, esteps=es[:nit.value].copy(), C=Cm, eps=eps, stats=_capi.stats())
 
 
 def rhf_grad(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
-             world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0):
+             world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None):
     """Energy and its gradient w.r.t. (alpha as passed, raw coefficients, Gaussian centres) in one fused pass:
     dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats)."""
     a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
     E, nit = C.c_double(0.0), C.c_int32(0)
     ga, gc, gx = np.zeros(a.nprim), np.zeros(a.nprim), np.zeros(3 * a.nbasis)
+    guess = None if guess_C is None else np.ascontiguousarray(guess_C, dtype=np.float64)
     opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce,
-                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold)
+                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess)
     st = _capi.check(_capi.lib().dq_rhf_grad(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), ga.ctypes, gc.ctypes,
                                              gx.ctypes), allow=(0, 1))
     return dict(E=E.value, status=st, niter=nit.value, grad=[ga, gc, gx], stats=_capi.stats())
@@ -59,13 +61,12 @@ def rhfenergy(alpha_old, coef2, xyz, l, charges, xyz_atom, natoms, nbasis, contr
               printguess, readguess, name, write, dtype, device=0):
     """Energy.py:75: returns E_elec + E_nuc, or 99999 when the SCF did not converge in max_scf iterations.
 
-    eigen=False (density purification) and readguess are dead / unreachable branches of the reference's public API
-     and are rejected."""
+    eigen=False (density purification) is a dead branch of the reference's public API
+    and is rejected; readguess (a .npy of C written by printguess) starts the SCF from that density (Energy.py:148-157)."""
     if not eigen:
         raise NotImplementedError("eigen=False (canonical purification) is unreachable through Tasks and not implemented")
-    if readguess is not None:
-        raise NotImplementedError("readguess warm start is not implemented")
-    r = rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=max_scf, log=log, device=device)
+    guess = np.load(readguess) if readguess is not None else None          # Energy.py:148-149
+    r = rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=max_scf, log=log, device=device, guess_C=guess)
     if printguess is not None:
         np.save(printguess, r["C"])  # Energy.py:197-198
     if r["status"] != 0:

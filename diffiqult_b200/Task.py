@@ -31,10 +31,11 @@ class _GradCache(object):
         self.key, self.val = None, None
 
     def get(self, args, device):
-        key = tuple(np.asarray(args[k], dtype=np.float64).tobytes() for k in (0, 1, 2)) + (int(args[10]), bool(args[12]))
+        key = tuple(np.asarray(args[k], dtype=np.float64).tobytes() for k in (0, 1, 2)) + (int(args[10]), bool(args[12]), args[15])
         if key != self.key:
+            guess = np.load(args[15]) if args[15] is not None else None     # readguess slot (Energy.py:148-149)
             r = _energy.rhf_grad(args[0], args[1], args[2], args[3], args[4], args[5], args[8], args[9],
-                                 max_scf=args[10], log=args[12], device=device)
+                                 max_scf=args[10], log=args[12], device=device, guess_C=guess)
             self.key, self.val = key, r
         return self.val
 
@@ -192,7 +193,12 @@ class Tasks(object):
         t0 = time.process_time()
         if not log and 0 in argnum:
             raise NotImplementedError("Opt on raw (non-log) exponents: _optupdateparam assumes log=True as in the reference")
-        args = self._energy_args(max_scf=max_scf, max_d=max_scf, log=log, printguess=None, readguess=None, name=taskname,
+        rguess = None
+        if readguess:   # Task.py:326-332 (fixed: the reference refers to an undefined max_d there and cannot run this branch)
+            rguess = taskname + '.npy'
+            if self._singlepoint(max_scf, max_scf, printcoef=True, name=taskname, output=False) == _energy.SCF_FAILED:
+                raise NameError('SCF did not converved')
+        args = self._energy_args(max_scf=max_scf, max_d=max_scf, log=log, printguess=None, readguess=rguess, name=taskname,
                                  write=False)
         grad_fun = function_grads_algopy(rhfenergy, argnum, device=self.device)
         res = self.select_method.get(method, self._BFGS)(rhfenergy, grad_fun, args, list(argnum), log, taskname, **otherargs)

@@ -498,8 +498,20 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   launch_eigh(side, n, 1, t1, vwork, L, wS, ework);
   launch_scale_cols_rsqrt(side, n, L, wS, t2);
   launch_gemm(side, false, true, n, n, n, t2, n, L, n, X, n, 1.0, 0.0);
-  CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, side));        // Energy.py:159 (core guess)
-  scf_pre(0, side);
+  // readguess (Energy.py:148-157): D0 = C0_occ C0_occ^T from the caller's coefficients, first Fock matrix H + G[D0]
+  const bool have_guess = opt && opt->guess_C != nullptr;
+  double* D0 = nullptr;
+  if (have_guess) {
+    std::vector<double> c0(nn);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) c0[(size_t)i * n + j] = opt->guess_C[(size_t)P.f_orig[i] * n + j];
+    double* dC0 = ws.upload(c0);
+    CU(cudaStreamSynchronize(st));      // c0 is a stack-scoped staging vector
+    D0 = ws.alloc<double>(nn);
+    launch_gemm(side, false, true, n, n, ne, dC0, n, dC0, n, D0, n, 1.0, 0.0);
+  } else {
+    CU(cudaMemcpyAsync(F, H, nn * sizeof(double), cudaMemcpyDeviceToDevice, side));      // Energy.py:159 (core guess)
+    scf_pre(0, side);
+  }
   CU(cudaEventRecord(ev_side, side));
 
   Timer t_eri(st);
@@ -509,6 +521,10 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
 
   Timer t_scf(st);
   CU(cudaStreamWaitEvent(st, ev_side, 0));
+  if (have_guess) {                      // the first Fock matrix needs the ERIs: no overlap for iteration 0
+    fock_build(P, jk, D0, H, F, nullptr);                                      // Energy.py:157
+    scf_pre(0, st);
+  }
   double oldE = 1e8, e_elec = 0.0;
   out.esteps.clear();
   out.converged = false;
@@ -555,8 +571,8 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     const int k = out.niter;
     double *Dbar = ws.alloc<double>(nn), *Hbar = ws.alloc<double>(nn), *Xbar = ws.alloc<double>(nn, true), *Pm = ws.alloc<double>(nn),
            *Fbar = ws.alloc<double>(nn), *Y = ws.alloc<double>(nn);
-    double* At = ws.alloc<double>((size_t)k * nn);
-    double* Bt = ws.alloc<double>((size_t)k * nn);
+    double* At = ws.alloc<double>((size_t)(k + 1) * nn);
+    double* Bt = ws.alloc<double>((size_t)(k + 1) * nn);
     int nterms = 0;
     launch_axpby(st, (int)nn, 2.0, hF[k - 1], 0.0, Dbar);
     launch_axpby(st, (int)nn, 2.0, hD[k - 1], 0.0, Hbar);
@@ -586,6 +602,10 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
         CU(cudaMemcpyAsync(Bt + (size_t)nterms * nn, hD[t - 2], nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
         ++nterms;
         fock_build(P, jk, Fbar, nullptr, nullptr, Dbar);                           // Dbar_{t-1} = G[Fbar]
+      } else if (have_guess) {             // F_0 = H + G[D0] with a parameter-independent D0: one more two-electron term
+        CU(cudaMemcpyAsync(At + (size_t)nterms * nn, Fbar, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(Bt + (size_t)nterms * nn, D0, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        ++nterms;
       }
     }
     // Sbar = L [ (L^T Xbar L) o Phi ] L^T

@@ -56,6 +56,8 @@ typedef struct dq_options {
   double screen_threshold; /* 0 (default): every quartet is evaluated, as in the reference, which screens nothing.
                             * > 0 (opt-in): a tile is skipped when 2 pi^(5/2) max|K_ab| max|K_cd| over its two block
                             * pairs is below the threshold (an upper bound of its primitive prefactors) */
+  const double* guess_C;   /* readguess (Energy.py:148-157): [nbasis*nbasis] AO x MO coefficients; the first Fock matrix is
+                            * built from D = C_occ C_occ^T instead of the core Hamiltonian.  NULL: core guess */
 } dq_options;
 
 typedef struct dq_stats {

@@ -113,6 +113,16 @@ def eri_index(i, j, k, l, n):
     return lib().orc_eri_index(C.c_int(i), C.c_int(j), C.c_int(k), C.c_int(l), C.c_int(n))
 
 
+def set_guess(C0):
+    """readguess (Energy.py:148-157): AO x MO matrix used to build the first Fock matrix, or None."""
+    global _guess_keep
+    _guess_keep = None if C0 is None else _f(C0)
+    lib().orc_set_guess(C.c_void_p(None) if C0 is None else _guess_keep.ctypes)
+
+
+_guess_keep = None
+
+
 def rhf(a, max_scf=100):
     """-> dict(E, status (0 converged / 1 not: the reference's 99999), niter, esteps, C, eps)."""
     n = a.nbasis

@@ -614,6 +614,7 @@ template <class T> static void transpose(int n, const T* A, T* At) {
 }
 
 struct ScfOut { int status; int niter; double esteps[1024]; double e_nuc; };
+static const double* g_guess_C = nullptr;   // readguess: AO x MO coefficients of a previous run (Energy.py:148-157), or null
 
 // Energy.py:75-199, 311-324 with eigen=True, readguess=None (the only branch Tasks reaches)
 template <class T> static T rhfenergy(const Sys& s, const T* alpha_in, const T* coef2, const V3<T>* xyz, int max_scf,
@@ -638,6 +639,11 @@ template <class T> static T rhfenergy(const Sys& s, const T* alpha_in, const T* 
   matmul(n, X.data(), LT.data(), X.data());
   transpose(n, X.data(), XT.data());
   std::vector<T> F(H), Fp((size_t)n * n), Cp((size_t)n * n), C((size_t)n * n), D((size_t)n * n), ev(n);
+  if (g_guess_C) {                                                                      // Energy.py:148-157
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) { double tmp = 0.0; for (int k = 0; k < s.ne; ++k) tmp = tmp + g_guess_C[i * n + k] * g_guess_C[j * n + k]; D[i * n + j] = T(tmp); }
+    fockmatrix(n, H.data(), eri.data(), D.data(), F.data());
+  }
   T OldE = T(1e8), E_elec = T(0.0);
   so->status = 0; so->niter = 0;
   for (int it = 0; it < max_scf; ++it) {
@@ -675,6 +681,7 @@ static Sys make_sys(int natoms, const int* charges, const double* atoms, int nba
 extern "C" {
 
 int orc_pmax(void) { return ORC_PMAX; }
+void orc_set_guess(const double* C) { g_guess_C = C; }
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -441,3 +441,34 @@ def test_molden_output_diffs_against_the_reference_file(golden, tmp_path):
     i = lines.index("[GTO]")
     gto = [tuple(float(x) for x in ln.split()) for ln in lines[i + 1:lines.index("[MO]")] if len(ln.split()) == 2 and "." in ln.split()[0]]
     assert np.abs(np.array(gto) - g["gto"]).max() < 1e-11
+
+
+def test_readguess_warm_start_vs_oracle(tmp_path):
+    """printguess / readguess (Energy.py:148-157,197-198): the SCF restarted from a saved C, energy and gradient against
+    the oracle run with the same guess (a slightly different geometry, so the guess is good but not converged)."""
+    s = sysmol("h2o_sto3g")
+    t = Tasks(s, str(tmp_path / "w"))
+    args = t._energy_args(max_scf=50, printguess=str(tmp_path / "c.npy"))
+    e0 = Energy.rhfenergy(*args)
+    C0 = np.load(str(tmp_path / "c.npy"))
+    assert C0.shape == (7, 7)
+    s2 = sysmol("h2o_sto3g")
+    s2.xyz = s2.xyz + 0.02 * np.random.default_rng(4).normal(size=s2.xyz.shape)
+    a = orc.SysArrays(s2)
+    args2 = (np.log(s2.alpha), s2.coef, s2.xyz, s2.l, s2.charges, s2.atom, s2.list_contr, s2.ne)
+    cold = Energy.rhf_grad(*args2, max_scf=50)
+    warm = Energy.rhf_grad(*args2, max_scf=50, guess_C=C0)
+    assert warm["status"] == 0 and warm["niter"] < cold["niter"]
+    orc.set_guess(C0)
+    try:
+        o = orc.rhf(a, max_scf=50)
+        assert o["niter"] == warm["niter"] and abs(o["E"] - warm["E"]) < TOL_E
+        for n in (0, 1, 2):
+            og = orc.rhf_grad(a, n, max_scf=50)
+            assert og["status"] == 0 and np.abs(og["grad"] - warm["grad"][n]).max() < TOL_G
+    finally:
+        orc.set_guess(None)
+    # through the reference-shaped entry point: readguess is a path to the .npy
+    t2 = Tasks(s2, str(tmp_path / "w2"))
+    e = Energy.rhfenergy(*t2._energy_args(max_scf=50, readguess=str(tmp_path / "c.npy")))
+    assert abs(e - warm["E"]) < 1e-12 and abs(e0 - e) > 1e-6
