@@ -30,6 +30,31 @@ sys.path.insert(0, ROOT)
 METRIC = "eri_plus_gradient_primitive_quartets_per_s"
 UNIT = "primitive quartets/s"
 FLOP_VALUE, FLOP_GRAD = 375.0, 1500.0   # algorithmic flop per primitive quartet
+REF_SAMPLE_WATERS = 3                   # --impl reference: (H2O)_3 per step, a few seconds on the host cores
+CPU_BASELINE_WATERS = 4                 # cpu_baseline of the default run: (H2O)_4, ~10-30 s of CPU work
+
+
+def executed_counts():
+    """ncu-counted FP64 work of the two tile kernels on THIS workload (profiles/fp64_executed.json, written by
+    scripts/fp64_executed.py from an ncu metrics pass of this same command): executed flop per primitive quartet and the
+    DRAM traffic per launch set.  None when the file is absent (the roofline then falls back to the algorithmic count)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_executed.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gbps", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "MEASURED_PEAKS.json %s (of measured)" % k
+    except Exception:
+        pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent on this box)"
 
 
 def workload(n_waters):
@@ -100,7 +125,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 2
+    sample = REF_SAMPLE_WATERS
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, e, cores = cpu_reference_step(sample)
@@ -178,7 +203,46 @@ def run_ours(args):
         K = args.steps
         ms_grad_kernel = float(np.mean([x["ms_eri_grad"] for x in stats]))
         ms_eri_kernel = float(np.mean([x["ms_eri"] for x in stats]))
-        achieved = st["n_prim_quartets"] * FLOP_GRAD / (ms_grad_kernel * 1e-3) * 1e-12
+        builds = max(st["fock_builds"], 1)
+        ms_jk_build = float(np.mean([x["ms_jk"] for x in stats])) / builds
+        npq = st["n_prim_quartets"]                      # primitive quartets this rank evaluates per ERI pass
+        alg_grad = npq * FLOP_GRAD / (ms_grad_kernel * 1e-3) * 1e-12
+        alg_eri = npq * FLOP_VALUE / (ms_eri_kernel * 1e-3) * 1e-12
+        ex = executed_counts()
+        if ex:
+            achieved = npq * ex["k_eri_grad_tiles"]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
+            ach_eri = npq * ex["k_eri_tiles"]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
+            basis = ("EXECUTED FP64 flop per primitive quartet on this workload (ncu smsp__sass_thread_inst_executed_op_"
+                     "{2*dfma,dmul,dadd}_pred_on summed over the 16 class launches, %s) x primitive quartets / live CUDA-event "
+                     "time of the 16 launches" % ex.get("source", "profiles/fp64_executed.json"))
+            traffic = ex["k_eri_grad_tiles"].get("dram_bytes_per_step")
+        else:
+            achieved, ach_eri, traffic = alg_grad, alg_eri, None
+            basis = "ALGORITHMIC flop (SURVEY.md 8d) - profiles/fp64_executed.json absent"
+        hbm_peak, hbm_src = measured_hbm_peak()
+        jk_bytes = st["n_tiles"] * 2048.0                # 8 B per stored contracted ERI, every tile read once per build
+        jk_gbs = jk_bytes / (ms_jk_build * 1e-3) * 1e-9 if ms_jk_build > 0 else 0.0
+        roofline = {
+            "kernel": "k_eri_grad_tiles<*> (16 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
+            "bound": "fp64", "bound_note": "FP64 CUDA-core pipe (neither HBM nor tensor cores bound this kernel: %s)" % (
+                "DRAM traffic %.2f GB per step" % (traffic * 1e-9) if traffic else "see profiles/"),
+            "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
+            "achieved_basis": basis,
+            "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry)",
+            "fp64_pipe_active_ncu": ex["k_eri_grad_tiles"].get("pipe_fp64_active_frac") if ex else None,
+            "algorithmic": {"flop_per_primitive_quartet": FLOP_GRAD, "achieved": alg_grad, "frac": alg_grad / peak.value,
+                            "note": "SURVEY.md 8(d) count of the reference's formulas (2.7 Boys calls x ~100 flop dominate); this "
+                                    "geometry is almost entirely in the t >= 50 regime where the reference's continued fraction "
+                                    "equals its closed form to the last bit, so far fewer flop are executed: frac > 1 here is not "
+                                    "a hardware statement, `frac` above is"},
+            "eri_value_kernel": {"kernel": "k_eri_tiles<*>", "achieved": ach_eri, "frac": ach_eri / peak.value,
+                                 "algorithmic_achieved": alg_eri,
+                                 "fp64_pipe_active_ncu": ex["k_eri_tiles"].get("pipe_fp64_active_frac") if ex else None},
+            "jk_kernel": {"kernel": "k_jk_chunks", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": jk_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_build": ms_jk_build, "builds_per_step": builds,
+                          "algorithmic_bytes_per_build": jk_bytes,
+                          "traffic": ex.get("k_jk_chunks", {}).get("dram_bytes_per_launch") if ex else None},
+        }
         h2d = int(lnalpha.nbytes + np.asarray(s.coef).nbytes + s.xyz.nbytes + 4 * (2 * s.nbasis + s.natoms) + s.atom.nbytes)
         d2h = int(8 * (1 + 2 * len(s.alpha) + 3 * s.nbasis) + 8 * (s.nbasis * s.nbasis + s.nbasis))
         line = {
@@ -197,20 +261,16 @@ def run_ours(args):
             "e2e": {"value": nq / (wall / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(np.sum([x["launches"] for x in stats])),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "k_eri_grad_tiles<*> (16 class launches per step)", "bound": "fp64", "achieved": achieved,
-                         "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
-                         "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry)",
-                         "algorithmic_flop_per_primitive_quartet": FLOP_GRAD,
-                         "eri_value_kernel": {"achieved": st["n_prim_quartets"] * FLOP_VALUE / (ms_eri_kernel * 1e-3) * 1e-12,
-                                              "algorithmic_flop_per_primitive_quartet": FLOP_VALUE}},
+            "roofline": roofline,
             "phases_ms": {k: float(np.mean([x[k] for x in stats])) for k in
-                          ("ms_setup", "ms_one_electron", "ms_eri", "ms_scf", "ms_reverse", "ms_eri_grad", "ms_grad_other", "ms_total")},
+                          ("ms_setup", "ms_one_electron", "ms_eri", "ms_scf", "ms_reverse", "ms_eri_grad", "ms_grad_other", "ms_jk", "ms_total")},
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, e, cores = cpu_reference_step(2)
+            v, dt, e, cores = cpu_reference_step(CPU_BASELINE_WATERS)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "(H2O)_2 STO-3G energy + forward-mode gradient argnum 0,1,2, C++/OpenMP port of the "
-                                              "reference algorithm, %.1f s" % dt}
+                                    "sample": "(H2O)_%d STO-3G (same cluster generator) energy + forward-mode gradient argnum 0,1,2: "
+                                              "C++/OpenMP port of the reference algorithm (oracle/rhf_oracle.cpp), %.1f s of CPU "
+                                              "work on %d threads" % (CPU_BASELINE_WATERS, dt, cores)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -370,11 +370,22 @@ static void unsort_matrix(const Prepared& P, const std::vector<double>& in, doub
 // G[D] = 2J - K from the stored tiles (+ allreduce of the partial J|K over ranks); F = H + G if F != null
 struct JK {
   double *JKacc;   // [2*n*n] J accumulators then K accumulators (one buffer: one allreduce)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // brackets of the contraction kernels, read by ms() after a sync
+  double ms() {
+    double tot = 0.0;
+    for (auto& e : ev) { float m = 0; if (cudaEventElapsedTime(&m, e.first, e.second) == cudaSuccess) tot += m; }
+    return tot;
+  }
+  ~JK() { for (auto& e : ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
 };
 static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, double* F, double* G) {
   const int n = P.N;
   cudaStream_t st = P.ws.st;
   CU(cudaMemsetAsync(jk.JKacc, 0, sizeof(double) * 2 * n * n, st));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  jk.ev.push_back({e0, e1});
+  CU(cudaEventRecord(e0, st));
   if (!P.direct) {
     launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
   } else {
@@ -394,6 +405,7 @@ static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, do
       }
     }
   }
+  CU(cudaEventRecord(e1, st));
   if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, P.ar_user);
   launch_fock_combine(st, n, P.d_fblock, H, jk.JKacc, jk.JKacc + (size_t)n * n, F, G);
   t_stats.fock_builds++;
@@ -653,6 +665,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     t_stats.n_tiles_skipped = (int64_t)sk;
   }
   CU(cudaStreamSynchronize(st));
+  t_stats.ms_jk = jk.ms();
   t_stats.ms_total = t_total.stop();
   t_stats.launches = launch_count();
 }

@@ -235,12 +235,27 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
   __syncthreads();
   double v = 0.0;
   if (c.valid) {
+    const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+    const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
     for (int pb = 0; pb < c.b1.KK; ++pb) {
-      const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+      const double* brec = sbra + pb * kPairFields * 16;
+      const PairPrim bra = load_pair(brec, c.bl);
+      // the components of P along the axes of the p functions come straight from the staged records at a CTA-uniform
+      // offset: no per-primitive select
+      double bs[4] = {0.0, 0.0, 0.0, 0.0};
+      if (LA) bs[0] = brec[ia * 16 + c.bl];
+      if (LB) bs[1] = brec[ib * 16 + c.bl];
+      if (LC) bs[2] = brec[ic * 16 + c.bl];
+      if (LD) bs[3] = brec[id * 16 + c.bl];
       for (int pk = 0; pk < c.b2.KK; ++pk) {
-        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
-        v += prim_quartet<LA, LB, LC, LD, false>(bra, ket, c.b1.axI, c.b1.axJ, c.b2.axI, c.b2.axJ, c_boys, 0.0, nullptr,
-                                                 nullptr, nullptr, nullptr, nullptr, nullptr);
+        const double* krec = sket + pk * kPairFields * 16;
+        const PairPrim ket = load_pair(krec, c.kt);
+        double ds[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
+        if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
+        if (LC) ds[2] = bs[2] - krec[ic * 16 + c.kt];
+        if (LD) ds[3] = bs[3] - krec[id * 16 + c.kt];
+        v += prim_quartet<LA, LB, LC, LD, false>(bra, ket, ds, dl, c_boys, 0.0, nullptr);
       }
     }
   }
@@ -422,6 +437,7 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
   }
 
   const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+  const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
   const long long off5b = c.b1.off / kPairFields * kAdjFields, off5k = c.b2.off / kPairFields * kAdjFields;
   double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
   for (int k0 = 0; k0 < KKk; k0 += KC) {
@@ -429,22 +445,47 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
     for (int x = 0; x < kn * kAdjFields; ++x) sacc[x * 256 + tid] = 0.0;
     __syncthreads();      // (first chunk: also publishes the staged pair records)
     for (int pb = 0; pb < KKb; ++pb) {
-      const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+      const double* brec = sbra + pb * kPairFields * 16;
+      const PairPrim bra = load_pair(brec, c.bl);
       PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
+      // adjoints of bra.P along the axes of the four p functions, summed over the ket primitives and folded into ba.P
+      // once per bra primitive (the axis is CTA-uniform: no select inside the ket loop)
+      double bsl[4] = {0.0, 0.0, 0.0, 0.0};
       if (W != 0.0) {
+        double bs[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LA) bs[0] = brec[ia * 16 + c.bl];
+        if (LB) bs[1] = brec[ib * 16 + c.bl];
+        if (LC) bs[2] = brec[ic * 16 + c.bl];
+        if (LD) bs[3] = brec[id * 16 + c.bl];
         for (int pk = 0; pk < kn; ++pk) {
-          const PairPrim ket = load_pair(sket + (k0 + pk) * kPairFields * 16, c.kt);
-          PairAdj ka; ka.P[0] = ka.P[1] = ka.P[2] = ka.g = ka.K = 0.0;
-          double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-          prim_quartet<LA, LB, LC, LD, true>(bra, ket, ia, ib, ic, id, c_boys, W, &ba, &ka, &e0, &e1, &e2, &e3);
-          if (LA) { add3(ba.P, ia, e0); pas += e0; }
-          if (LB) { add3(ba.P, ib, e1); pbs += e1; }
-          if (LC) { add3(ka.P, ic, e2); qcs += e2; }
-          if (LD) { add3(ka.P, id, e3); qds += e3; }
+          const double* krec = sket + (k0 + pk) * kPairFields * 16;
+          const PairPrim ket = load_pair(krec, c.kt);
+          double ds[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
+          if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
+          if (LC) ds[2] = bs[2] - krec[ic * 16 + c.kt];
+          if (LD) ds[3] = bs[3] - krec[id * 16 + c.kt];
+          QuartetAdj q;
+          prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
+          ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
+          if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }      // bra.pa = bra.P[ia] - A[ia]
+          if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
+          if (LC) { bsl[2] += q.ds[2]; qcs += q.e[2]; }
+          if (LD) { bsl[3] += q.ds[3]; qds += q.e[3]; }
+          // ket adjoints: per-thread shared-memory slots [P0 P1 P2 g K] of this ket primitive; the axis components go to
+          // the row of their axis (CTA-uniform row index)
           double* a = sacc + (pk * kAdjFields) * 256 + tid;
-          a[0] += ka.P[0]; a[256] += ka.P[1]; a[512] += ka.P[2]; a[768] += ka.g; a[1024] += ka.K;
+          a[0] -= q.dP[0]; a[256] -= q.dP[1]; a[512] -= q.dP[2]; a[768] += q.gk; a[1024] += q.Kk;
+          if (LA) a[ia * 256] -= q.ds[0];
+          if (LB) a[ib * 256] -= q.ds[1];
+          if (LC) a[ic * 256] += q.e[2] - q.ds[2];                     // ket.pa = ket.P[ic] - C[ic]
+          if (LD) a[id * 256] += q.e[3] - q.ds[3];
         }
       }
+      if (LA) add3(ba.P, ia, bsl[0]);
+      if (LB) add3(ba.P, ib, bsl[1]);
+      if (LC) add3(ba.P, ic, bsl[2]);
+      if (LD) add3(ba.P, id, bsl[3]);
       // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
       double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
 #pragma unroll

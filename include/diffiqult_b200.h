@@ -73,6 +73,7 @@ typedef struct dq_stats {
   int32_t grad_terms;      /* rank of the two-particle weight used by the ERI-gradient pass */
   int32_t jk_direct;       /* 1 if the Fock builds were integral-direct, 0 if they used the stored tiles */
   int64_t n_tiles_skipped; /* tiles skipped by the opt-in screening in the (last) ERI pass */
+  double ms_jk;            /* sum of the J/K contraction kernels' times over all Fock builds (CUDA events, read once at the end) */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):

@@ -11,11 +11,11 @@ static void init() { if (!g_init) { boys_const_init(&g_bc); g_init = true; } }
 
 template <bool LA, bool LB, bool LC, bool LD>
 static double run(const PairPrim& bra, const PairPrim& ket, const int* l, double w, PairAdj* ba, PairAdj* ka, double* e) {
-  return prim_quartet<LA, LB, LC, LD, true>(bra, ket, l[0] - 1, l[1] - 1, l[2] - 1, l[3] - 1, g_bc, w, ba, ka, e, e + 1, e + 2, e + 3);
+  return prim_quartet_axes<LA, LB, LC, LD, true>(bra, ket, l[0] - 1, l[1] - 1, l[2] - 1, l[3] - 1, g_bc, w, ba, ka, e);
 }
 template <bool LA, bool LB, bool LC, bool LD>
 static double runv(const PairPrim& bra, const PairPrim& ket, const int* l) {
-  return prim_quartet<LA, LB, LC, LD, false>(bra, ket, l[0] - 1, l[1] - 1, l[2] - 1, l[3] - 1, g_bc, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return prim_quartet_axes<LA, LB, LC, LD, false>(bra, ket, l[0] - 1, l[1] - 1, l[2] - 1, l[3] - 1, g_bc, 0.0, nullptr, nullptr, nullptr);
 }
 
 extern "C" {
