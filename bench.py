@@ -238,7 +238,7 @@ def run_ours(args):
             "eri_value_kernel": {"kernel": "k_eri_tiles<*>", "achieved": ach_eri, "frac": ach_eri / peak.value,
                                  "algorithmic_achieved": alg_eri,
                                  "fp64_pipe_active_ncu": ex["k_eri_tiles"].get("pipe_fp64_active_frac") if ex else None},
-            "jk_kernel": {"kernel": "k_jk_chunks", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "jk_kernel": {"kernel": "k_jk_cols", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
                           "frac": jk_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_build": ms_jk_build, "builds_per_step": builds,
                           "algorithmic_bytes_per_build": jk_bytes,
                           "traffic": ex.get("k_jk_chunks", {}).get("dram_bytes_per_launch") if ex else None},

@@ -394,6 +394,141 @@ __global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tile
 }
 
 // ---------------------------------------------------------------------------------------------
+// J/K contraction, column-owner form (the default).  Same chunks, same strips, same weights as k_jk_chunks above, but no
+// per-tile CTA barrier and no digest warps: every WARP streams its own share of the chunk, two tiles per step, one LANE per
+// ket pair (k,l) of a tile.  The lane reads the 16 bra-pair values of its column (coalesced: 16 lanes x 8 B per row of
+// the tile) and owns them in registers:
+//   J[k,l]   = sum_ij D_ij v            complete in the lane: one global atomic
+//   J[i,j]  += D_kl v                   16 register accumulators kept for the whole chunk, reduced once at the end
+//   K[i,k], K[i,l], K[j,k], K[j,l]      4 partial sums each, reduce-scattered over the 4 lanes that share k (or l) with
+//                                       3 shuffles, so that every lane ends with ONE complete value and adds it to the
+//                                       shared-memory row strips K[I,:], K[J,:]
+// 96 FMAs per lane and tile-column: 1536 per tile as before, now spread over all lanes with the loads of 16 warps in
+// flight per SM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double reduce_scatter4(double a0, double a1, double a2, double a3, int hi, int lo, int mhi, int mlo) {
+  // 4 lanes differing in the lane bits (mhi, mlo) hold 4 partial sums each; returns, in the lane with (hi, lo), the
+  // complete sum number 2*hi + lo
+  const double s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
+  double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, mhi);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, mhi);
+  const double s = lo ? k0 : k1;
+  double k = lo ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, s, mlo);
+  return k;
+}
+
+__global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
+                                                    const double* __restrict__ store, const double* __restrict__ D,
+                                                    double* __restrict__ Jacc, double* __restrict__ Kacc) {
+  extern __shared__ double sm[];
+  const int n = s.N, tid = threadIdx.x;
+  const int ns = n | 1;
+  double* dstrip = sm;                  // [8][ns]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
+  double* kstrip = sm + 8 * ns;         // [8][ns]
+  double* sdij = kstrip + 8 * ns;       // [16]
+  JkDesc* desc = (JkDesc*)(sdij + 16);  // [256]
+  const int2 ch = chunks[blockIdx.x];
+  const int bp1 = tiles[ch.x].bp1;
+  const BlockPair b1 = s.bp[bp1];
+  const bool dIJ = b1.bI == b1.bJ;
+  if (tid < ch.y) {
+    const int bp2 = tiles[ch.x + tid].bp2;
+    const BlockPair b2 = s.bp[bp2];
+    JkDesc d; d.sK = b2.sI; d.sL = b2.sJ; d.nK = (short)b2.nI; d.nL = (short)b2.nJ; d.same_bp = bp2 == bp1; d.dKL = b2.bI == b2.bJ;
+    d.skip = tile_screened(s, tiles[ch.x + tid]); d.pad_ = 0;
+    desc[tid] = d;
+  }
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const bool isJ = row >= 4;
+    const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
+    dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
+    kstrip[x] = 0.0;
+  }
+  if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, kl = lane & 15, k = kl >> 2, l = kl & 3;
+  int per = (ch.y + 7) >> 3;
+  per += per & 1;                       // whole two-tile steps per warp
+  const int tb = warp * per, te = min(ch.y, tb + per);
+  double jacc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) jacc[q] = 0.0;
+  for (int t0 = tb; t0 < te; t0 += 2) {
+    const int t = t0 + h;
+    JkDesc d = desc[t < te ? t : tb];
+    const bool act = t < te && !d.skip;
+    const bool inb = act && k < d.nK && l < d.nL;
+    double v[16];
+    const double* src = store + (long long)(ch.x + t) * kTile + kl;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = act ? src[q * 16] : 0.0;
+    const double dkl = inb ? D[(d.sK + k) * n + d.sL + l] : 0.0;
+    const double wS = d.same_bp ? 0.5 : 1.0;
+    const bool dKL = d.dKL != 0;
+    const double jw = wS * (dKL ? 1.0 : 2.0) * dkl;
+    double jkl = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { jacc[q] = fma(jw, v[q], jacc[q]); jkl = fma(sdij[q], v[q], jkl); }
+    if (inb && jkl != 0.0) atomicAdd(Jacc + (d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl);
+    // exchange: D of the OTHER bra block at the lane's ket column / row
+    const int ck = d.sK + k, cl = d.sL + l;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = fma(dJl, v[i * 4 + j], a[i]); b[i] = fma(dJk, v[i * 4 + j], b[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double dIl = dstrip[i * ns + cl], dIk = dstrip[i * ns + ck];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[i * 4 + j], c[j]); e[j] = fma(dIk, v[i * 4 + j], e[j]); }
+    }
+    const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
+    // K[i,k] (sum over j,l): lanes sharing k differ in l = lane bits 1,0 -> this lane ends with i = l
+    const double kik = reduce_scatter4(a[0], a[1], a[2], a[3], l >> 1, l & 1, 2, 1);
+    // K[i,l] (sum over j,k): lanes sharing l differ in k = lane bits 3,2 -> i = k
+    const double kil = reduce_scatter4(b[0], b[1], b[2], b[3], k >> 1, k & 1, 8, 4);
+    const double kjk = reduce_scatter4(c[0], c[1], c[2], c[3], l >> 1, l & 1, 2, 1);     // j = l
+    const double kjl = reduce_scatter4(e[0], e[1], e[2], e[3], k >> 1, k & 1, 8, 4);     // j = k
+    if (act) {
+      if (k < d.nK) {
+        if (kik != 0.0) atomicAdd(kstrip + l * ns + ck, w * kik);
+        if (kjk != 0.0) atomicAdd(kstrip + (4 + l) * ns + ck, w * kjk);
+      }
+      if (l < d.nL) {
+        if (kil != 0.0) atomicAdd(kstrip + k * ns + cl, w * kil);
+        if (kjl != 0.0) atomicAdd(kstrip + (4 + k) * ns + cl, w * kjl);
+      }
+    }
+  }
+  // J[i,j]: sum the 16 accumulators over the 32 lanes of the warp
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) jacc[q] += __shfl_xor_sync(0xffffffffu, jacc[q], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if ((q >> 2) < b1.nI && (q & 3) < b1.nJ && jacc[q] != 0.0) atomicAdd(Jacc + (b1.sI + (q >> 2)) * n + b1.sJ + (q & 3), jacc[q]);
+  }
+  __syncthreads();
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const double val = kstrip[x];
+    if (val != 0.0) {
+      const int row = x / ns, col = x - row * ns, r = row & 3;
+      atomicAdd(Kacc + ((row >= 4 ? b1.sJ : b1.sI) + r) * n + col, val);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kGradKetChunk = 9;   // ket primitive pairs whose adjoint slots are resident at once
 
 // ERI gradient: sum over the tile's quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
@@ -1023,7 +1158,12 @@ void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, in
   const size_t smem = ((size_t)16 * (s.N | 1) + 2 * 16 * 17 + 16) * sizeof(double) + 256 * 16;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(k_jk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-  k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+  static const bool old_kernel = getenv("DQ_JK_DIGEST") != nullptr;   // A/B switch: the per-tile digest kernel
+  if (old_kernel) { k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED(); return; }
+  const size_t smem2 = ((size_t)16 * (s.N | 1) + 16) * sizeof(double) + 256 * 16;
+  static size_t attr2 = 0;
+  if (smem2 > 48 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_jk_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); attr2 = smem2; }
+  k_jk_cols<<<nchunks, 256, smem2, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
 }
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
                      double* g_xyz) {
