@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_lib", "libdiffiqult_b200.so")
-SOURCES = ["dq_kernels.cu", "dq_api.cu"]
+SOURCES = ["dq_kernels.cu", "dq_batch.cu", "dq_api.cu"]
 HEADERS = ["dq_math.cuh", "dq_layout.h", "dq_launch.h", os.path.join("..", "..", "include", "diffiqult_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 

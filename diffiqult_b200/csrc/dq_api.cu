@@ -670,6 +670,144 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   t_stats.launches = launch_count();
 }
 
+// ---------------------------------------------------------------------------------------------
+// batch of molecules of one structure (dq_batch.cu): host side
+// ---------------------------------------------------------------------------------------------
+static void run_batch(const dq_system* shape, int nmol, const double* atoms, const double* alpha, const double* coef, const double* xyz,
+                      const dq_options* opt, bool want_grad, double* E, int32_t* status, int32_t* niter, double* g_alpha,
+                      double* g_coef, double* g_xyz) {
+  memset(&t_stats, 0, sizeof t_stats);
+  reset_batch_launch_count();
+  check_system(shape);
+  if (nmol <= 0) fail(-1, "nmol must be positive");
+  const int n = shape->nbasis, nprim = shape->nprim, natoms = shape->natoms, ne = shape->ne;
+  if (ne <= 0 || ne > n) fail(-1, "ne (doubly-occupied orbitals) must be in 1..nbasis");
+  if (n > 40) fail(-4, "the batched small-molecule path holds the SCF in shared memory: nbasis <= 40 (use the per-molecule entry points)");
+  const int dev = opt ? opt->device : 0;
+  need_device(dev);
+  const int max_scf = (opt && opt->max_scf > 0) ? opt->max_scf : 30;
+  const double tol = (opt && opt->e_tol > 0) ? opt->e_tol : 1e-8;
+  cudaStream_t st = opt ? (cudaStream_t)opt->stream : 0;
+  static thread_local int boys_dev = -1;
+  if (boys_dev != dev) { if (upload_boys_constants_batch() != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
+  Timer t_total(st);
+
+  // structure tables
+  const int nn = n * n, M = n * (n + 1) / 2, neri = M * (M + 1) / 2;
+  std::vector<int> foff(n + 1, 0), ftype(n), Z(natoms > 0 ? natoms : 1, 0);
+  for (int i = 0; i < n; ++i) { foff[i + 1] = foff[i] + shape->contr[i]; ftype[i] = shape->ltype[i]; }
+  for (int a = 0; a < natoms; ++a) Z[a] = shape->charges[a];
+  std::vector<int2> pairs(M);
+  std::vector<int> poff(M + 1, 0), recp;
+  int kkmax = 0;
+  {
+    int x = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i; j < n; ++j, ++x) {
+        pairs[x] = make_int2(i, j);
+        const int kk = shape->contr[i] * shape->contr[j];
+        poff[x + 1] = poff[x] + kk;
+        kkmax = std::max(kkmax, kk);
+        for (int q = 0; q < kk; ++q) recp.push_back(x);
+      }
+  }
+  const int nrec = poff[M];
+  if (kkmax > 40) fail(-4, "the batched path keeps ket adjoints in shared memory: at most 40 primitive pairs per function pair");
+  std::vector<std::vector<int2>> qcls(16);
+  long long npq = 0;
+  for (int x = 0; x < M; ++x)
+    for (int y = x; y < M; ++y) {
+      const int cls = (ftype[pairs[x].x] > 0) * 8 + (ftype[pairs[x].y] > 0) * 4 + (ftype[pairs[y].x] > 0) * 2 + (ftype[pairs[y].y] > 0);
+      qcls[cls].push_back(make_int2(x, y));
+      npq += (long long)(poff[x + 1] - poff[x]) * (poff[y + 1] - poff[y]);
+    }
+  std::vector<int2> qlist; int qstart[17];
+  for (int c = 0; c < 16; ++c) { qstart[c] = (int)qlist.size(); qlist.insert(qlist.end(), qcls[c].begin(), qcls[c].end()); }
+  qstart[16] = (int)qlist.size();
+
+  // molecules are processed in slabs so that the SCF history of a slab stays within a fixed budget
+  const size_t per_mol = sizeof(double) * ((size_t)nrec * (kPairFields + kAdjFields) + (size_t)neri + (size_t)8 * nn +
+                                           (want_grad ? (size_t)max_scf * (4 * nn + n) + (size_t)(max_scf + 1) * 2 * nn : 0) + 4 * nprim);
+  size_t fre = 0, tot = 0;
+  CU(cudaMemGetInfo(&fre, &tot));
+  const size_t budget = std::min<size_t>((fre + g_pool.cached_bytes) / 2, (size_t)16 << 30);
+  const int slab = (int)std::max<size_t>(1, std::min<size_t>((size_t)nmol, budget / std::max<size_t>(per_mol, 1)));
+
+  Workspace ws; ws.dev = dev; ws.st = st;
+  int* d_foff = ws.upload(foff); int* d_ftype = ws.upload(ftype); int* d_Z = ws.upload(Z);
+  int2* d_pairs = ws.upload(pairs); int* d_poff = ws.upload(poff); int* d_recp = ws.upload(recp);
+  int2* d_qlist = ws.upload(qlist);
+  CU(cudaStreamSynchronize(st));           // the staging vectors above live on this stack frame
+  const size_t hl = (size_t)max_scf * (4 * nn + n);
+  for (int m0 = 0; m0 < nmol; m0 += slab) {
+    const int nm = std::min(slab, nmol - m0);
+    Workspace w2; w2.dev = dev; w2.st = st;
+    auto up = [&](const double* h, size_t cnt) {
+      double* d = w2.alloc<double>(cnt);
+      CU(cudaMemcpyAsync(d, h, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+      return d;
+    };
+    BatchDev b;
+    b.nmol = nm; b.N = n; b.nprim = nprim; b.natoms = natoms; b.M = M; b.nrec = nrec; b.neri = neri; b.kkmax = kkmax; b.ne = ne;
+    b.f_off = d_foff; b.f_type = d_ftype; b.Z = d_Z; b.pairs = d_pairs; b.pair_off = d_poff; b.rec_pair = d_recp;
+    b.atoms = up(atoms + (size_t)m0 * natoms * 3, (size_t)nm * std::max(natoms, 1) * 3);
+    b.xyz = up(xyz + (size_t)m0 * n * 3, (size_t)nm * n * 3);
+    b.craw = up(coef + (size_t)m0 * nprim, (size_t)nm * nprim);
+    const double* d_alpha_in = up(alpha + (size_t)m0 * nprim, (size_t)nm * nprim);
+    b.alpha = w2.alloc<double>((size_t)nm * nprim); b.cn = w2.alloc<double>((size_t)nm * nprim);
+    b.prec = w2.alloc<double>((size_t)nrec * kPairFields * nm);
+    double *S = w2.alloc<double>((size_t)nm * nn), *H = w2.alloc<double>((size_t)nm * nn), *eri = w2.alloc<double>((size_t)nm * neri);
+    double *Eel = w2.alloc<double>(nm), *esteps = w2.alloc<double>((size_t)nm * max_scf), *C = w2.alloc<double>((size_t)nm * nn),
+           *eps = w2.alloc<double>((size_t)nm * n);
+    int *d_niter = w2.alloc<int>(nm), *d_conv = w2.alloc<int>(nm), *d_nterms = w2.alloc<int>(nm);
+    double *hist = nullptr, *terms = nullptr, *Hbar = nullptr, *Sbar = nullptr;
+    if (want_grad) {
+      hist = w2.alloc<double>((size_t)nm * hl); terms = w2.alloc<double>((size_t)nm * (max_scf + 1) * 2 * nn);
+      Hbar = w2.alloc<double>((size_t)nm * nn); Sbar = w2.alloc<double>((size_t)nm * nn);
+    }
+    Timer t_e(st);
+    launch_batch_prepare(st, b, d_alpha_in, shape->log_alpha != 0);
+    launch_batch_one_electron(st, b, S, H);
+    for (int c = 0; c < 16; ++c) launch_batch_eri(st, c, b, d_qlist + qstart[c], qstart[c + 1] - qstart[c], eri);
+    t_stats.ms_eri += t_e.stop();
+    Timer t_s(st);
+    if (launch_batch_scf(st, b, S, H, eri, max_scf, tol, want_grad ? 1 : 0, hist, Eel, d_niter, d_conv, esteps, C, eps, terms, d_nterms,
+                         Hbar, Sbar) != 0)
+      fail(-4, "basis too large for the shared-memory SCF kernel of the batched path");
+    t_stats.ms_scf += t_s.stop();
+    std::vector<double> hE(nm); std::vector<int> hn(nm), hc(nm);
+    CU(cudaMemcpyAsync(hE.data(), Eel, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hn.data(), d_niter, nm * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hc.data(), d_conv, nm * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (want_grad) {
+      Timer t_g(st);
+      double* padj = w2.alloc<double>((size_t)nrec * kAdjFields * nm, true);
+      double* pasum = w2.alloc<double>((size_t)M * 2 * nm, true);
+      double *ga = w2.alloc<double>((size_t)nm * nprim, true), *gc = w2.alloc<double>((size_t)nm * nprim, true),
+             *gx = w2.alloc<double>((size_t)nm * n * 3, true), *graw = w2.alloc<double>((size_t)nm * nprim);
+      for (int c = 0; c < 16; ++c)
+        launch_batch_eri_grad(st, c, b, d_qlist + qstart[c], qstart[c + 1] - qstart[c], terms, d_nterms, max_scf, padj, pasum);
+      launch_batch_grad_finish(st, b, shape->log_alpha != 0, padj, pasum, Sbar, Hbar, ga, gc, gx, graw);
+      if (g_alpha) CU(cudaMemcpyAsync(g_alpha + (size_t)m0 * nprim, ga, (size_t)nm * nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (g_coef) CU(cudaMemcpyAsync(g_coef + (size_t)m0 * nprim, graw, (size_t)nm * nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (g_xyz) CU(cudaMemcpyAsync(g_xyz + (size_t)m0 * n * 3, gx, (size_t)nm * n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      t_stats.ms_eri_grad += t_g.stop();
+    }
+    CU(cudaStreamSynchronize(st));
+    for (int m = 0; m < nm; ++m) {
+      dq_system one = *shape;
+      one.atoms = atoms + (size_t)(m0 + m) * natoms * 3;
+      if (E) E[m0 + m] = hE[m] + nuclear_repulsion(&one);                        // Energy.py:196
+      if (status) status[m0 + m] = hc[m] ? 0 : 1;                                // 1 = the reference's 99999 sentinel
+      if (niter) niter[m0 + m] = hn[m];
+    }
+  }
+  t_stats.n_quartets = (int64_t)qlist.size() * nmol;
+  t_stats.n_prim_quartets = npq * nmol;
+  t_stats.ms_total = t_total.stop();
+  t_stats.launches = batch_launch_count();
+}
+
 }  // namespace dq
 
 // =============================================================================================
@@ -808,6 +946,14 @@ int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t*
     if (niter) *niter = o.niter;
     return o.converged ? 0 : 1;
   } catch (const Fail& f) { return f.code; } catch (const std::exception& e) { t_err = e.what(); return -9; }
+}
+
+int dq_rhf_grad_batch(const dq_system* shape, int32_t nmol, const double* atoms, const double* alpha, const double* coef,
+                      const double* xyz, const dq_options* opt, int32_t want_grad, double* E, int32_t* status, int32_t* niter,
+                      double* g_alpha, double* g_coef, double* g_xyz) {
+  DQ_TRY
+  run_batch(shape, nmol, atoms, alpha, coef, xyz, opt, want_grad != 0, E, status, niter, g_alpha, g_coef, g_xyz);
+  DQ_CATCH
 }
 
 int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int32_t device) {

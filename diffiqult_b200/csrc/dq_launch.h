@@ -47,4 +47,20 @@ void launch_mul(cudaStream_t st, int n, const double* a, const double* b, double
 void launch_boys(cudaStream_t st, int n, const double* t, double* F, double* dF);
 void launch_fp64_peak(cudaStream_t st, int blocks, int iters, double* out);
 
+// batched small-molecule path (dq_batch.cu)
+int upload_boys_constants_batch();
+long long batch_launch_count();
+void reset_batch_launch_count();
+void launch_batch_prepare(cudaStream_t st, const BatchDev& b, const double* alpha_in, int log_alpha);
+void launch_batch_one_electron(cudaStream_t st, const BatchDev& b, double* S, double* H);
+void launch_batch_eri(cudaStream_t st, int cls, const BatchDev& b, const int2* qlist, int nq, double* eri);
+size_t batch_scf_smem_bytes(int n, int neri, bool eri_in_smem);
+int launch_batch_scf(cudaStream_t st, const BatchDev& b, const double* S, const double* H, const double* eri, int max_scf, double tol,
+                     int want_grad, double* hist, double* Eelec, int* niter, int* conv, double* esteps, double* C, double* eps,
+                     double* terms, int* nterms, double* Hbar, double* Sbar);
+void launch_batch_eri_grad(cudaStream_t st, int cls, const BatchDev& b, const int2* qlist, int nq, const double* terms, const int* nterms,
+                           int max_scf, double* padj, double* pasum);
+void launch_batch_grad_finish(cudaStream_t st, const BatchDev& b, int log_alpha, const double* padj, const double* pasum, const double* Sbar,
+                              const double* Hbar, double* ga, double* gc, double* gx, double* graw);
+
 }  // namespace dq

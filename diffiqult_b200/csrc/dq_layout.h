@@ -6,6 +6,7 @@
 // of a 256-thread CTA, all of one angular class, so a CTA never diverges on the integral class.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace dq {
 
@@ -45,6 +46,25 @@ struct SystemDev {
   const double* bp_kmax;   // [nbp]  max |K_ab| over the primitive-pair records of each block pair
   double screen;           // opt-in tile screening threshold (0: off)
   unsigned long long* skipped;   // counter of skipped tiles (screening on)
+};
+
+// Batch of molecules of ONE structure (dq_batch.cu).  Functions stay in the caller's order; function pairs x = (i <= j)
+// in the reference's packed order (Tools.py:17-22).  Inputs are per molecule ([mol][...]); the primitive-pair records and
+// their adjoints are molecule-fastest ([...][mol]) because the quartet kernels put neighbouring molecules in neighbouring lanes.
+struct BatchDev {
+  int nmol, N, nprim, natoms, M, nrec, neri, kkmax, ne;
+  const int* f_off;        // [N+1]
+  const int* f_type;       // [N]  0 s, 1..3 p
+  const int* Z;            // [natoms]
+  const int2* pairs;       // [M]  (i, j), i <= j
+  const int* pair_off;     // [M+1] first primitive-pair record of each function pair
+  const int* rec_pair;     // [nrec] function pair of each record
+  const double* atoms;     // [nmol][natoms*3]
+  const double* xyz;       // [nmol][N*3]
+  const double* craw;      // [nmol][nprim] raw contraction coefficients
+  double* alpha;           // [nmol][nprim] exponents (after exp() when the caller passes ln alpha)
+  double* cn;              // [nmol][nprim] normalised coefficients
+  double* prec;            // [nrec][kPairFields][nmol]
 };
 
 }  // namespace dq

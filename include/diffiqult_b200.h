@@ -108,6 +108,17 @@ int dq_rhf(const dq_system* sys, const dq_options* opt, double* E, int32_t* nite
 int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha,
                 double* g_coef, double* g_xyz);
 
+/* Batch of `nmol` molecules of ONE structure (shape: natoms, charges, nbasis, contr, ltype, nprim, ne, log_alpha; its
+ * atoms/alpha/coef/xyz pointers are ignored): the reference evaluates such a batch as nmol separate
+ * Tasks.runtask('Energy'|'Grad') calls (Task.py:242-278, 223-240).  Per-molecule inputs: atoms [nmol][natoms*3],
+ * alpha [nmol][nprim] (ln alpha if shape->log_alpha), coef [nmol][nprim] raw, xyz [nmol][nbasis*3].  Outputs: E [nmol],
+ * status [nmol] (0 converged / 1 = 99999 sentinel), niter [nmol] and, when want_grad, the three gradient groups
+ * [nmol][nprim], [nmol][nprim], [nmol][nbasis*3] (any may be NULL).  Every molecule follows its own truncated SCF exactly
+ * as dq_rhf_grad does.  nbasis <= 40, at most 40 primitive pairs per function pair (status -4 otherwise). */
+int dq_rhf_grad_batch(const dq_system* shape, int32_t nmol, const double* atoms, const double* alpha, const double* coef,
+                      const double* xyz, const dq_options* opt, int32_t want_grad, double* E, int32_t* status, int32_t* niter,
+                      double* g_alpha, double* g_coef, double* g_xyz);
+
 /* Eigen.py:69-74 eigensolver on plain doubles: batch of symmetric n x n matrices -> ascending eigenvalues
  * w[batch*n], eigenvectors in the columns of V[batch*n*n]. */
 int dq_eigh(int32_t n, int32_t batch, const double* A, double* w, double* V, int32_t device);

@@ -1,0 +1,52 @@
+"""profiles/fp64_executed.json from an ncu metrics pass over the ERI tile kernels and the J/K kernel of one bench step.
+
+On the GPU box (after the same command has exited 0 without ncu):
+    ncu --clock-control none --csv --log-file gpurun_out/fp64.csv -k regex:'k_eri_(grad_)?tiles|k_jk_cols' -c 33 --metrics \
+      smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,\
+      smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,\
+      smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,\
+      dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,launch__registers_per_thread \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline
+Here:  python scripts/fp64_executed.py gpurun_out/fp64.csv <primitive quartets evaluated per pass (dq_stats.n_prim_quartets)>
+"""
+import collections
+import csv
+import json
+import shutil
+import sys
+
+src, npq = sys.argv[1], float(sys.argv[2])
+rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"')) if len(r) > 14 and r[0] != "ID"]
+per = collections.OrderedDict()
+for r in rows:
+    per.setdefault((r[0], r[4].split("(")[0].replace("void ", "")), {})[r[12]] = float(r[14].replace(",", ""))
+fam = {}
+for (_, name), m in per.items():
+    f = name.split("<")[0]
+    a = fam.setdefault(f, {"launches": 0, "flop": 0.0, "inst": 0.0, "ns": 0.0, "pipe_ns": 0.0, "dram": 0.0})
+    dfma = m.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0.0)
+    dmul = m.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", 0.0)
+    dadd = m.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", 0.0)
+    ns = m["gpu__time_duration.sum"]
+    a["launches"] += 1
+    a["flop"] += 2 * dfma + dmul + dadd
+    a["inst"] += dfma + dmul + dadd
+    a["ns"] += ns
+    a["pipe_ns"] += ns * m.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 0.0) / 100.0
+    a["dram"] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
+out = {"source": "profiles/r1_fp64_executed.csv (ncu metrics pass of `bench.py --steps 1 --warmup 1`, first step)",
+       "primitive_quartets_evaluated_per_pass": npq}
+for f, a in fam.items():
+    e = {"launches": a["launches"], "ms_under_ncu": a["ns"] * 1e-6, "executed_flop": a["flop"],
+         "executed_fp64_thread_instructions": a["inst"], "pipe_fp64_active_frac": a["pipe_ns"] / a["ns"],
+         "executed_tflops_under_ncu": a["flop"] / a["ns"] * 1e-3}
+    if f in ("k_eri_tiles", "k_eri_grad_tiles"):
+        e["flop_per_primitive_quartet"] = a["flop"] / npq
+        e["fp64_instructions_per_primitive_quartet"] = a["inst"] / npq
+        e["dram_bytes_per_step"] = a["dram"]
+    else:
+        e["dram_bytes_per_launch"] = a["dram"] / a["launches"]
+    out[f] = e
+json.dump(out, open("profiles/fp64_executed.json", "w"), indent=1)
+shutil.copy(src, "profiles/r1_fp64_executed.csv")
+print(json.dumps(out, indent=1))

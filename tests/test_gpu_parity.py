@@ -491,3 +491,57 @@ def test_real_multi_gpu_nccl_sharding():
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
     rep = json.loads(line)
     assert rep["ok"] and rep["world"] == 2 and rep["allreduce_calls"] > 0
+
+
+def test_fused_batch_path_vs_oracle_and_per_molecule_path():
+    """BASELINE config 5 through the fused device path (csrc/dq_batch.cu: thread per (quartet, molecule), one CTA per
+    molecule for the SCF + reverse sweep): 24 perturbed CH4 / STO-3G.  Energies, iteration counts and all three
+    gradient groups against the oracle (3 molecules) and against the per-molecule kernels (all molecules)."""
+    from diffiqult_b200 import batch
+    mols = synthetic.perturbed_methanes(24)
+    syss = [System_mol(m, basis_set_3G_STO, 10, "ch4_%d" % i) for i, m in enumerate(mols)]
+    E, status, grads, st = batch.rhf_grad_batch_fused(syss, max_scf=50)
+    assert (status == 0).all() and st["launches"] < 40
+    for i in (0, 7, 23):
+        a = orc.SysArrays(syss[i])
+        o = orc.rhf(a, max_scf=50)
+        assert o["niter"] == st["niter"][i] and abs(E[i] - o["E"]) < TOL_E
+        for n in (0, 1, 2):
+            og = orc.rhf_grad(a, n, max_scf=50)
+            assert og["status"] == 0 and np.abs(grads[i][n] - og["grad"]).max() < TOL_G
+    for i, s in enumerate(syss):
+        r = Energy.rhf_grad(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=50)
+        assert r["niter"] == st["niter"][i] and abs(r["E"] - E[i]) < 1e-11
+        for n in range(3):
+            assert np.abs(r["grad"][n] - grads[i][n]).max() < 1e-10
+    # energy-only mode, and the dispatcher picks the fused path for a one-structure batch
+    E2, status2, g2 = batch.rhf_grad_batch(syss[:5], max_scf=50, with_grad=False)
+    assert g2 is None and np.abs(E2 - E[:5]).max() < 1e-12
+
+
+def test_fused_batch_other_structures_and_failure_sentinel():
+    """The fused path on other shapes: formaldehyde (N = 12, mixed s/p classes incl. (pp|pp)), water with the uncontracted
+    test basis (one primitive per function, N = 14), and a batch in which max_scf is too small (status 1 = 99999)."""
+    from diffiqult_b200 import batch
+    rng = np.random.default_rng(11)
+    for name, max_scf in (("ch2o", 100), ("h2o", 60)):
+        mol, basis, ne = systems.SYSTEMS[name]
+        syss = []
+        for r in range(3):
+            m2 = [(z, tuple(np.array(p) + 0.03 * rng.normal(size=3))) for z, p in mol]
+            syss.append(System_mol(m2, basis, ne, name))
+        E, status, grads, st = batch.rhf_grad_batch_fused(syss, max_scf=max_scf)
+        for i, s in enumerate(syss):
+            a = orc.SysArrays(s)
+            o = orc.rhf(a, max_scf=max_scf)
+            assert status[i] == o["status"] and st["niter"][i] == o["niter"] and abs(E[i] - o["E"]) < TOL_E
+            if o["status"] == 0:
+                for n in (0, 2):
+                    og = orc.rhf_grad(a, n, max_scf=max_scf)
+                    assert np.abs(grads[i][n] - og["grad"]).max() < TOL_G
+    syss = [System_mol(m, basis_set_3G_STO, 10, "ch4") for m in synthetic.perturbed_methanes(4)]
+    E, status, grads, st = batch.rhf_grad_batch_fused(syss, max_scf=3)
+    assert (status == 1).all() and (st["niter"] == 3).all()
+    with pytest.raises(_capi.DiffiqultB200Error, match="nbasis <= 40"):
+        big = [System_mol(synthetic.water_cluster(8), basis_set_3G_STO, 80, "w8")] * 2
+        batch.rhf_grad_batch_fused(big, max_scf=5)
