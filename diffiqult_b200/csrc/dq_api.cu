@@ -115,9 +115,20 @@ struct TilePlan {
   int cls_start[17];
   int chunk_cls_start[17];      // chunk ranges per class
   long long n_quartets = 0, n_prim_quartets = 0;
+  // the same tiles re-ordered for the gradient pass: per class by KET block pair, cut into chunks sharing the ket
+  std::vector<Tile> gtiles;
+  std::vector<int2> gchunks;
+  int gchunk_cls_start[17];
   Tile* d_tiles = nullptr;
   int2* d_chunks = nullptr;
-  ~TilePlan() { if (d_tiles) cudaFree(d_tiles); if (d_chunks) cudaFree(d_chunks); }
+  Tile* d_gtiles = nullptr;
+  int2* d_gchunks = nullptr;
+  ~TilePlan() {
+    if (d_tiles) cudaFree(d_tiles);
+    if (d_chunks) cudaFree(d_chunks);
+    if (d_gtiles) cudaFree(d_gtiles);
+    if (d_gchunks) cudaFree(d_gchunks);
+  }
 };
 static thread_local std::shared_ptr<TilePlan> t_plan;
 
@@ -306,7 +317,25 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       }
     }
     tp->chunk_cls_start[16] = (int)tp->chunks.size();
+    constexpr int kGradChunk = 12;
+    tp->gtiles = tp->tiles;
+    for (int c = 0; c < 16; ++c) {
+      std::stable_sort(tp->gtiles.begin() + tp->cls_start[c], tp->gtiles.begin() + tp->cls_start[c + 1],
+                       [](const Tile& a, const Tile& b) { return a.bp2 < b.bp2; });
+      tp->gchunk_cls_start[c] = (int)tp->gchunks.size();
+      for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
+        int e = t + 1;
+        while (e < tp->cls_start[c + 1] && e - t < kGradChunk && tp->gtiles[e].bp2 == tp->gtiles[t].bp2) ++e;
+        tp->gchunks.push_back(make_int2(t, e - t));
+        t = e;
+      }
+    }
+    tp->gchunk_cls_start[16] = (int)tp->gchunks.size();
     if (!P.plan_only) {
+      CU(cudaMalloc(&tp->d_gtiles, std::max<size_t>(tp->gtiles.size(), 1) * sizeof(Tile)));
+      CU(cudaMalloc(&tp->d_gchunks, std::max<size_t>(tp->gchunks.size(), 1) * sizeof(int2)));
+      CU(cudaMemcpyAsync(tp->d_gtiles, tp->gtiles.data(), tp->gtiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(tp->d_gchunks, tp->gchunks.data(), tp->gchunks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
       CU(cudaMalloc(&tp->d_tiles, std::max<size_t>(tp->tiles.size(), 1) * sizeof(Tile)));
       CU(cudaMalloc(&tp->d_chunks, std::max<size_t>(tp->chunks.size(), 1) * sizeof(int2)));
       CU(cudaMemcpyAsync(tp->d_tiles, tp->tiles.data(), tp->tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
@@ -639,8 +668,9 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
     Timer t_gk(st);
     for (int c = 0; c < 16; ++c)
-      launch_eri_grad_tiles(st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd, nterms, At, Bt,
-                            padj, pasum, P.kkmax);
+      launch_eri_grad_chunks(st, c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c],
+                             P.tp->gchunk_cls_start[c + 1] - P.tp->gchunk_cls_start[c], P.sd, P.d_pd, nterms, At, Bt, padj, pasum,
+                             P.kkmax);
     t_stats.ms_eri_grad = t_gk.stop();
     launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
     if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);

@@ -6,7 +6,7 @@
 //   k_eri_tiles<class>              contracted ERIs, one 256-quartet tile per CTA       (Integrals.py:190-401)
 //   k_scatter_packed                tile store -> the reference's packed Eri_vec order  (Tools.py:17-51)
 //   k_jk_chunks                     J/K contraction of the stored tiles with D          (Energy.py:29-38)
-//   k_eri_grad_tiles<class>         sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode
+//   k_eri_grad_chunks<class>        sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode, chunks of tiles sharing the ket
 //   k_pair_bwd                      pair-field adjoints -> exponents, coefficients, centres
 //   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
 #include <cuda_runtime.h>
@@ -531,112 +531,141 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
 // ---------------------------------------------------------------------------------------------
 constexpr int kGradKetChunk = 9;   // ket primitive pairs whose adjoint slots are resident at once
 
-// ERI gradient: sum over the tile's quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
+// ERI gradient: sum over the quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
 //   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
 // where sum_terms <A, dG[B]> is the two-electron part of dE from the SCF reverse sweep.
+//
+// One CTA walks a CHUNK of tiles that share the KET block pair (the gradient pass does not touch the tile store, so its
+// tiles are re-ordered by ket).  The ket records are staged once and the per-thread ket-adjoint slots in shared memory
+// accumulate over the whole chunk; they are summed over the 16 bra lanes and flushed once per chunk.  Inside the chunk
+// there is NO CTA barrier: a warp = 2 bra lanes x 16 ket lanes reads its bra records straight from global memory (L1/L2
+// resident, 16 lanes per address), reduces its bra adjoints with shuffles and moves on to the next tile on its own.
+// (With one tile per CTA the 8 warps drifted apart over the 81 primitive quartets of a tile and ~10 % of the stall
+// samples sat on the end-of-tile barrier.)
 // ---------------------------------------------------------------------------------------------
-// occupancy: up to three p functions the kernel fits two CTAs per SM (128 registers with <= 40 B of spills, 2 x 112 KB
-// shared memory); (pp|pp) needs 226 registers and gains nothing from being squeezed (measured)
+// occupancy: up to three p functions the kernel fits two CTAs per SM (128 registers with small spills, 2 x ~105 KB
+// shared memory); (pp|pp) needs > 200 registers and gains nothing from being squeezed (measured)
 template <bool LA, bool LB, bool LC, bool LD>
 __global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
-k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd, int nterms,
-                 const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
-                 double* __restrict__ pasum) {
+k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s, const double* __restrict__ pd,
+                  int nterms, const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
+                  double* __restrict__ pasum) {
   extern __shared__ double sm[];
-  const Tile tl = tiles[blockIdx.x];
-  if (tile_screened(s, tl)) return;
-  const TileCtx c = tile_ctx(tl, s);
+  const int2 ch = chunks[blockIdx.x];
+  const int bp2 = tiles[ch.x].bp2;
+  const BlockPair b2 = s.bp[bp2];
   const int tid = threadIdx.x;
-  const int KKb = c.b1.KK, KKk = c.b2.KK;
-  double* sbra = sm;
-  double* sket = sbra + KKb * kPairFields * 16;
+  const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
+  const int KKk = b2.KK;
+  double* sket = sm;
   // ket adjoints accumulate in per-thread shared-memory slots; long contractions are walked in chunks of kGradKetChunk
   // ket primitive pairs so that the slots stay within shared memory (STO-3G: 9 pairs = one chunk)
   double* sacc = sket + KKk * kPairFields * 16;     // [(min(KKk, kGradKetChunk)*5 + 2)][256]
   const int KC = KKk < kGradKetChunk ? KKk : kGradKetChunk;
-  stage_pairs(c, pd, sbra, sket);
-
-  double W = 0.0;
-  if (c.valid) {
-    const int n = s.N;
-    const int i = c.b1.sI + c.il, j = c.b1.sJ + c.jl, k = c.b2.sI + c.kl, l = c.b2.sJ + c.ll;
-    const size_t nn = (size_t)n * n;
-    for (int t = 0; t < nterms; ++t) {
-      const double* A = At + t * nn;
-      const double* B = Bt + t * nn;
-      W += 8.0 * (A[i * n + j] * B[k * n + l] + A[k * n + l] * B[i * n + j]) -
-           2.0 * (A[i * n + k] * B[j * n + l] + A[j * n + k] * B[i * n + l] + A[i * n + l] * B[j * n + k] +
-                  A[j * n + l] * B[i * n + k]);
-    }
-    W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (c.b1.bI == c.b1.bJ ? 0.5 : 1.0) * (c.b2.bI == c.b2.bJ ? 0.5 : 1.0);
+  {
+    const double* gk = pd + b2.off * 16;
+    for (int x = tid; x < KKk * kPairFields * 16; x += 256) sket[x] = gk[x];
   }
-
-  const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
-  const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
-  const long long off5b = c.b1.off / kPairFields * kAdjFields, off5k = c.b2.off / kPairFields * kAdjFields;
-  double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
+  const int n = s.N;
+  const size_t nn = (size_t)n * n;
+  const int ic = b2.axI, id = b2.axJ;
+  const int k = b2.sI + kl, l = b2.sJ + ll;
+  const bool kvalid = kl < b2.nI && ll < b2.nJ;
+  const long long off5k = b2.off / kPairFields * kAdjFields;
+  double qcs = 0.0, qds = 0.0;
   for (int k0 = 0; k0 < KKk; k0 += KC) {
     const int kn = KKk - k0 < KC ? KKk - k0 : KC;
     for (int x = 0; x < kn * kAdjFields; ++x) sacc[x * 256 + tid] = 0.0;
-    __syncthreads();      // (first chunk: also publishes the staged pair records)
-    for (int pb = 0; pb < KKb; ++pb) {
-      const double* brec = sbra + pb * kPairFields * 16;
-      const PairPrim bra = load_pair(brec, c.bl);
-      PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
-      // adjoints of bra.P along the axes of the four p functions, summed over the ket primitives and folded into ba.P
-      // once per bra primitive (the axis is CTA-uniform: no select inside the ket loop)
-      double bsl[4] = {0.0, 0.0, 0.0, 0.0};
-      if (W != 0.0) {
-        double bs[4] = {0.0, 0.0, 0.0, 0.0};
-        if (LA) bs[0] = brec[ia * 16 + c.bl];
-        if (LB) bs[1] = brec[ib * 16 + c.bl];
-        if (LC) bs[2] = brec[ic * 16 + c.bl];
-        if (LD) bs[3] = brec[id * 16 + c.bl];
-        for (int pk = 0; pk < kn; ++pk) {
-          const double* krec = sket + (k0 + pk) * kPairFields * 16;
-          const PairPrim ket = load_pair(krec, c.kt);
-          double ds[4] = {0.0, 0.0, 0.0, 0.0};
-          if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
-          if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
-          if (LC) ds[2] = bs[2] - krec[ic * 16 + c.kt];
-          if (LD) ds[3] = bs[3] - krec[id * 16 + c.kt];
-          QuartetAdj q;
-          prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
-          ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
-          if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }      // bra.pa = bra.P[ia] - A[ia]
-          if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
-          if (LC) { bsl[2] += q.ds[2]; qcs += q.e[2]; }
-          if (LD) { bsl[3] += q.ds[3]; qds += q.e[3]; }
-          // ket adjoints: per-thread shared-memory slots [P0 P1 P2 g K] of this ket primitive; the axis components go to
-          // the row of their axis (CTA-uniform row index)
-          double* a = sacc + (pk * kAdjFields) * 256 + tid;
-          a[0] -= q.dP[0]; a[256] -= q.dP[1]; a[512] -= q.dP[2]; a[768] += q.gk; a[1024] += q.Kk;
-          if (LA) a[ia * 256] -= q.ds[0];
-          if (LB) a[ib * 256] -= q.ds[1];
-          if (LC) a[ic * 256] += q.e[2] - q.ds[2];                     // ket.pa = ket.P[ic] - C[ic]
-          if (LD) a[id * 256] += q.e[3] - q.ds[3];
+    __syncthreads();      // (first round: also publishes the staged ket records)
+    for (int ti = 0; ti < ch.y; ++ti) {
+      const Tile tl = tiles[ch.x + ti];
+      if (tile_screened(s, tl)) continue;
+      const BlockPair b1 = s.bp[tl.bp1];
+      const int KKb = b1.KK;
+      const int ia = b1.axI, ib = b1.axJ;
+      const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+      double W = 0.0;
+      if (kvalid && il < b1.nI && jl < b1.nJ) {
+        const int i = b1.sI + il, j = b1.sJ + jl;
+        for (int t = 0; t < nterms; ++t) {
+          const double* A = At + t * nn;
+          const double* B = Bt + t * nn;
+          W += 8.0 * (A[i * n + j] * B[k * n + l] + A[k * n + l] * B[i * n + j]) -
+               2.0 * (A[i * n + k] * B[j * n + l] + A[j * n + k] * B[i * n + l] + A[i * n + l] * B[j * n + k] +
+                      A[j * n + l] * B[i * n + k]);
+        }
+        W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (b1.bI == b1.bJ ? 0.5 : 1.0) * (b2.bI == b2.bJ ? 0.5 : 1.0);
+      }
+      const long long off5b = b1.off / kPairFields * kAdjFields;
+      const double* gbra = pd + b1.off * 16;
+      double pas = 0.0, pbs = 0.0;
+      for (int pb = 0; pb < KKb; ++pb) {
+        const double* brec = gbra + pb * kPairFields * 16;
+        PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
+        // adjoints of bra.P along the axes of the four p functions, summed over the ket primitives and folded into ba.P
+        // once per bra primitive (the axis is CTA-uniform: no select inside the ket loop)
+        double bsl[4] = {0.0, 0.0, 0.0, 0.0};
+        if (W != 0.0) {
+          const PairPrim bra = load_pair(brec, bl);
+          double bs[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) bs[0] = brec[ia * 16 + bl];
+          if (LB) bs[1] = brec[ib * 16 + bl];
+          if (LC) bs[2] = brec[ic * 16 + bl];
+          if (LD) bs[3] = brec[id * 16 + bl];
+          for (int pk = 0; pk < kn; ++pk) {
+            const double* krec = sket + (k0 + pk) * kPairFields * 16;
+            const PairPrim ket = load_pair(krec, kt);
+            double ds[4] = {0.0, 0.0, 0.0, 0.0};
+            if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
+            if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
+            if (LC) ds[2] = bs[2] - krec[ic * 16 + kt];
+            if (LD) ds[3] = bs[3] - krec[id * 16 + kt];
+            QuartetAdj q;
+            prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
+            ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
+            if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }      // bra.pa = bra.P[ia] - A[ia]
+            if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
+            if (LC) { bsl[2] += q.ds[2]; qcs += q.e[2]; }
+            if (LD) { bsl[3] += q.ds[3]; qds += q.e[3]; }
+            // ket adjoints: per-thread shared-memory slots [P0 P1 P2 g K] of this ket primitive; the axis components go
+            // to the row of their axis (CTA-uniform row index)
+            double* a = sacc + (pk * kAdjFields) * 256 + tid;
+            a[0] -= q.dP[0]; a[256] -= q.dP[1]; a[512] -= q.dP[2]; a[768] += q.gk; a[1024] += q.Kk;
+            if (LA) a[ia * 256] -= q.ds[0];
+            if (LB) a[ib * 256] -= q.ds[1];
+            if (LC) a[ic * 256] += q.e[2] - q.ds[2];                     // ket.pa = ket.P[ic] - C[ic]
+            if (LD) a[id * 256] += q.e[3] - q.ds[3];
+          }
+        }
+        if (LA) add3(ba.P, ia, bsl[0]);
+        if (LB) add3(ba.P, ib, bsl[1]);
+        if (LC) add3(ba.P, ic, bsl[2]);
+        if (LD) add3(ba.P, id, bsl[3]);
+        // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
+        double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
+#pragma unroll
+        for (int f = 0; f < kAdjFields; ++f) {
+#pragma unroll
+          for (int o = 8; o >= 1; o >>= 1) r[f] += __shfl_xor_sync(0xffffffffu, r[f], o);
+        }
+        if (kt == 0) {
+#pragma unroll
+          for (int f = 0; f < kAdjFields; ++f)
+            if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + bl, r[f]);
         }
       }
-      if (LA) add3(ba.P, ia, bsl[0]);
-      if (LB) add3(ba.P, ib, bsl[1]);
-      if (LC) add3(ba.P, ic, bsl[2]);
-      if (LD) add3(ba.P, id, bsl[3]);
-      // bra adjoints of this primitive pair: reduce over the 16 ket lanes of the half-warp
-      double r[kAdjFields] = {ba.P[0], ba.P[1], ba.P[2], ba.g, ba.K};
+      if (LA || LB) {
 #pragma unroll
-      for (int f = 0; f < kAdjFields; ++f) {
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) r[f] += __shfl_xor_sync(0xffffffffu, r[f], o);
-      }
-      if (c.kt == 0) {
-#pragma unroll
-        for (int f = 0; f < kAdjFields; ++f)
-          if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + c.bl, r[f]);
+        for (int o = 8; o >= 1; o >>= 1) { pas += __shfl_xor_sync(0xffffffffu, pas, o); pbs += __shfl_xor_sync(0xffffffffu, pbs, o); }
+        if (kt == 0) {
+          if (pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas);
+          if (pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs);
+        }
       }
     }
     const bool last = k0 + kn >= KKk;
     int nslots = kn * kAdjFields;
-    if (last) {           // the two contracted (Q-C), (Q-D) sums ride along with the last chunk
+    if (last) {           // the two contracted (Q-C), (Q-D) sums ride along with the last round
       sacc[(nslots + 0) * 256 + tid] = qcs;
       sacc[(nslots + 1) * 256 + tid] = qds;
       nslots += 2;
@@ -646,19 +675,13 @@ k_eri_grad_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __re
     for (int slot = tid >> 4; slot < nslots; slot += 16) {
       double sum = 0.0;
 #pragma unroll
-      for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + c.kt];
+      for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + kt];
       if (sum != 0.0) {
-        if (slot < kn * kAdjFields) atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + slot) * 16 + c.kt, sum);
-        else atomicAdd(pasum + ((long long)tl.bp2 * 2 + (slot - kn * kAdjFields)) * 16 + c.kt, sum);
+        if (slot < kn * kAdjFields) atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + slot) * 16 + kt, sum);
+        else atomicAdd(pasum + ((long long)bp2 * 2 + (slot - kn * kAdjFields)) * 16 + kt, sum);
       }
     }
     __syncthreads();
-  }
-#pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) { pas += __shfl_xor_sync(0xffffffffu, pas, o); pbs += __shfl_xor_sync(0xffffffffu, pbs, o); }
-  if (c.kt == 0) {
-    if (pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + c.bl, pas);
-    if (pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + c.bl, pbs);
   }
 }
 
@@ -1104,15 +1127,15 @@ static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemD
   k_eri_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
 }
 template <bool A, bool B, bool C, bool D>
-static void grad_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
-                        const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
+static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
+                        int nterms, const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_eri_grad_tiles<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs x 112 KB
+    cudaFuncSetAttribute(k_eri_grad_chunks<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_eri_grad_chunks<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs x ~105 KB
     attr = true;
   }
-  k_eri_grad_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
+  k_eri_grad_chunks<A, B, C, D><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
 }
 
 #define DQ_CLASS_SWITCH(cls, CALL)                                                              \
@@ -1135,17 +1158,17 @@ void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
 }
-void launch_eri_grad_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, int nterms,
-                           const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
-  if (nt <= 0) return;
+void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
+                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
+  if (nchunks <= 0) return;
   const size_t smem = eri_grad_smem_bytes(kkmax);
-#define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, nt, s, pd, nterms, At, Bt, padj, pasum, smem)
+#define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, nterms, At, Bt, padj, pasum, smem)
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
 }
 size_t eri_grad_smem_bytes(int kkmax) {
   const int kc = kkmax < kGradKetChunk ? kkmax : kGradKetChunk;
-  return ((size_t)2 * kkmax * kPairFields * 16 + (size_t)(kc * kAdjFields + 2) * 256) * sizeof(double);
+  return ((size_t)kkmax * kPairFields * 16 + (size_t)(kc * kAdjFields + 2) * 256) * sizeof(double);
 }
 void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
                            double* packed) {
