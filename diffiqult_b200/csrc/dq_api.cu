@@ -104,6 +104,29 @@ struct Timer {
   double stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
 };
 
+// The class launches of an ERI pass are independent of each other: they are issued on a few side streams forked from the
+// caller's stream and joined back, so that the last wave of one class overlaps the first of the next (with chunks of 12
+// tiles a gradient CTA lives ~1 ms, and a rank of an 8-GPU job has only ~10 waves per class).
+struct ForkJoin {
+  static constexpr int kSide = 4;
+  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  int dev = -1;
+  void init(int d) {
+    if (dev == d) return;
+    for (int i = 0; i < kSide; ++i) {
+      cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    dev = d;
+  }
+  void begin(cudaStream_t main) { cudaEventRecord(fork, main); for (int i = 0; i < kSide; ++i) cudaStreamWaitEvent(side[i], fork, 0); }
+  cudaStream_t lane(int i) const { return side[i % kSide]; }
+  void end(cudaStream_t main) { for (int i = 0; i < kSide; ++i) { cudaEventRecord(join[i], side[i]); cudaStreamWaitEvent(main, join[i], 0); } }
+};
+static thread_local ForkJoin t_fork;
+
 // Tile lists depend only on the basis STRUCTURE (types, contraction lengths) and on (world, rank), not on the
 // parameter values: each host thread keeps the last plan, so the repeated calls of an optimisation or of the bench
 // neither rebuild nor re-upload the 1.27 M-entry tile list.
@@ -317,7 +340,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       }
     }
     tp->chunk_cls_start[16] = (int)tp->chunks.size();
-    constexpr int kGradChunk = 12;
+    const int kGradChunk = getenv("DQ_GRAD_CHUNK") ? std::max(1, atoi(getenv("DQ_GRAD_CHUNK"))) : 12;
     tp->gtiles = tp->tiles;
     for (int c = 0; c < 16; ++c) {
       std::stable_sort(tp->gtiles.begin() + tp->cls_start[c], tp->gtiles.begin() + tp->cls_start[c + 1],
@@ -383,9 +406,14 @@ static void setup_jk_mode(Prepared& P, const dq_options* opt) {
 static void compute_eri_store(Prepared& P) {
   if (P.direct) return;
   P.d_store = P.ws.alloc<double>((size_t)P.ntiles * kTile);
-  for (int c = 0; c < 16; ++c)
-    launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
+  t_fork.init(P.ws.dev);
+  t_fork.begin(P.ws.st);
+  for (int c = 15, lane = 0; c >= 0; --c) {        // p-rich (long) classes first
+    if (P.cls_start[c + 1] == P.cls_start[c]) continue;
+    launch_eri_tiles(t_fork.lane(lane++), c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
                      P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
+  }
+  t_fork.end(P.ws.st);
 }
 
 // unsort an N x N matrix (rows and/or columns) into the caller's ordering
@@ -667,10 +695,15 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     double* gbuf = ws.alloc<double>((size_t)2 * P.nprim + 3 * n, true);
     double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
     Timer t_gk(st);
-    for (int c = 0; c < 16; ++c)
-      launch_eri_grad_chunks(st, c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c],
-                             P.tp->gchunk_cls_start[c + 1] - P.tp->gchunk_cls_start[c], P.sd, P.d_pd, nterms, At, Bt, padj, pasum,
-                             P.kkmax);
+    t_fork.init(ws.dev);
+    t_fork.begin(st);
+    for (int c = 15, lane = 0; c >= 0; --c) {
+      const int nch = P.tp->gchunk_cls_start[c + 1] - P.tp->gchunk_cls_start[c];
+      if (nch <= 0) continue;
+      launch_eri_grad_chunks(t_fork.lane(lane++), c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c], nch, P.sd, P.d_pd,
+                             nterms, At, Bt, padj, pasum, P.kkmax);
+    }
+    t_fork.end(st);
     t_stats.ms_eri_grad = t_gk.stop();
     launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
     if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);
