@@ -57,10 +57,13 @@ def measured_hbm_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent on this box)"
 
 
+SPACING = 24.0      # bohr; --spacing overrides (kernel studies on denser, non-converging clusters)
+
+
 def workload(n_waters):
     from diffiqult_b200 import System_mol, synthetic
     from diffiqult_b200.Basis import basis_set_3G_STO
-    mol = synthetic.water_cluster(n_waters)
+    mol = synthetic.water_cluster(n_waters, spacing=SPACING)
     return System_mol(mol, basis_set_3G_STO, 10 * n_waters, "w%d" % n_waters)
 
 
@@ -166,7 +169,7 @@ def run_ours(args):
     nq = prim_quartets(s)
     lnalpha = np.log(s.alpha)
     stream = distributed.current_stream_handle()
-    kw = dict(max_scf=100, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce, jk_mode=args.jk_mode,
+    kw = dict(max_scf=args.max_scf, device=local, stream=stream, world_size=world, rank=rank, allreduce=allreduce, jk_mode=args.jk_mode,
               screen_threshold=args.screen)
 
     def step():
@@ -208,14 +211,15 @@ def run_ours(args):
         npq = st["n_prim_quartets"]                      # primitive quartets this rank evaluates per ERI pass
         alg_grad = npq * FLOP_GRAD / (ms_grad_kernel * 1e-3) * 1e-12
         alg_eri = npq * FLOP_VALUE / (ms_eri_kernel * 1e-3) * 1e-12
-        ex = executed_counts()
+        # the ncu counts are data dependent: they hold for the default workload only
+        ex = executed_counts() if (args.spacing == 24.0 and args.waters == 32 and args.screen <= 0) else None
         if ex:
-            achieved = npq * ex["k_eri_grad_tiles"]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
+            achieved = npq * ex["k_eri_grad_chunks"]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
             ach_eri = npq * ex["k_eri_tiles"]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
             basis = ("EXECUTED FP64 flop per primitive quartet on this workload (ncu smsp__sass_thread_inst_executed_op_"
                      "{2*dfma,dmul,dadd}_pred_on summed over the 16 class launches, %s) x primitive quartets / live CUDA-event "
                      "time of the 16 launches" % ex.get("source", "profiles/fp64_executed.json"))
-            traffic = ex["k_eri_grad_tiles"].get("dram_bytes_per_step")
+            traffic = ex["k_eri_grad_chunks"].get("dram_bytes_per_step")
         else:
             achieved, ach_eri, traffic = alg_grad, alg_eri, None
             basis = "ALGORITHMIC flop (SURVEY.md 8d) - profiles/fp64_executed.json absent"
@@ -223,13 +227,13 @@ def run_ours(args):
         jk_bytes = st["n_tiles"] * 2048.0                # 8 B per stored contracted ERI, every tile read once per build
         jk_gbs = jk_bytes / (ms_jk_build * 1e-3) * 1e-9 if ms_jk_build > 0 else 0.0
         roofline = {
-            "kernel": "k_eri_grad_tiles<*> (16 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
+            "kernel": "k_eri_grad_chunks<*> (16 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
             "bound": "fp64", "bound_note": "FP64 CUDA-core pipe (neither HBM nor tensor cores bound this kernel: %s)" % (
                 "DRAM traffic %.2f GB per step" % (traffic * 1e-9) if traffic else "see profiles/"),
             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
             "achieved_basis": basis,
             "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry)",
-            "fp64_pipe_active_ncu": ex["k_eri_grad_tiles"].get("pipe_fp64_active_frac") if ex else None,
+            "fp64_pipe_active_ncu": ex["k_eri_grad_chunks"].get("pipe_fp64_active_frac") if ex else None,
             "algorithmic": {"flop_per_primitive_quartet": FLOP_GRAD, "achieved": alg_grad, "frac": alg_grad / peak.value,
                             "note": "SURVEY.md 8(d) count of the reference's formulas (2.7 Boys calls x ~100 flop dominate); this "
                                     "geometry is almost entirely in the t >= 50 regime where the reference's continued fraction "
@@ -250,6 +254,7 @@ def run_ours(args):
             "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "(H2O)_%d STO-3G RHF energy + full parameter gradient (argnum 0,1,2)" % args.waters,
+                       "grid_spacing_bohr": args.spacing,
                        "n_basis": int(s.nbasis), "n_primitives": int(len(s.alpha)), "primitive_quartets": nq,
                        "scf_iterations": st["scf_iterations"], "converged": r["status"] == 0, "energy_hartree": r["E"],
                        "jk_mode": ("integral-direct (tiles recomputed in every Fock build)" if st["jk_direct"] else
@@ -285,8 +290,13 @@ def main():
     ap.add_argument("--waters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])
+    ap.add_argument("--spacing", type=float, default=24.0, help="grid spacing of the water cluster in bohr (default 24: the "
+                    "densest grid on which the reference's plain Roothaan iteration converges; smaller values are kernel studies)")
+    ap.add_argument("--max-scf", type=int, default=100)
     ap.add_argument("--screen", type=float, default=0.0, help="opt-in tile screening threshold (default 0: evaluate everything, as the reference)")
     args = ap.parse_args()
+    global SPACING
+    SPACING = args.spacing
     if args.impl == "reference":
         run_reference(args)
     else:

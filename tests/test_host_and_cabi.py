@@ -166,3 +166,21 @@ def test_two_rank_allreduce_plumbing_over_gloo():
         assert buf == (np.arange(10) * 3.0).tolist()
         assert cnt == [whole["tiles"], whole["quartets"], whole["prim_quartets"]]
         assert ncalls == 2
+
+
+def test_batch_host_logic():
+    """diffiqult_b200.batch: structure test that gates the fused device path, and the contiguous rank slices (config 5)."""
+    from diffiqult_b200 import batch
+    ch4 = [System_mol(m, basis_set_3G_STO, 10, "ch4") for m in synthetic.perturbed_methanes(3)]
+    assert batch.same_structure(ch4)
+    h2o = System_mol(synthetic.H2O, basis_set_3G_STO, 10, "h2o")
+    assert not batch.same_structure(ch4 + [h2o])
+    cover = []
+    for r in range(8):
+        cover += list(batch.shard(1024, 8, r))
+    assert cover == list(range(1024)) and len(batch.shard(1024, 8, 3)) == 128
+    assert [len(batch.shard(10, 4, r)) for r in range(4)] == [3, 3, 3, 1]
+    # without a GPU the fused entry point refuses like every other one (no CPU fallback)
+    if _capi.lib().dq_device_count() == 0:
+        with pytest.raises(_capi.DiffiqultB200Error, match="no CUDA device"):
+            batch.rhf_grad_batch_fused(ch4, max_scf=5)
