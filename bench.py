@@ -217,8 +217,8 @@ def run_ours(args):
             achieved = npq * ex["k_eri_grad_chunks"]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
             ach_eri = npq * ex["k_eri_tiles"]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
             basis = ("EXECUTED FP64 flop per primitive quartet on this workload (ncu smsp__sass_thread_inst_executed_op_"
-                     "{2*dfma,dmul,dadd}_pred_on summed over the 16 class launches, %s) x primitive quartets / live CUDA-event "
-                     "time of the 16 launches" % ex.get("source", "profiles/fp64_executed.json"))
+                     "{2*dfma,dmul,dadd}_pred_on summed over the 7 class launches, %s) x primitive quartets / live CUDA-event "
+                     "time of those launches" % ex.get("source", "profiles/fp64_executed.json"))
             traffic = ex["k_eri_grad_chunks"].get("dram_bytes_per_step")
         else:
             achieved, ach_eri, traffic = alg_grad, alg_eri, None
@@ -227,7 +227,7 @@ def run_ours(args):
         jk_bytes = st["n_tiles"] * 2048.0                # 8 B per stored contracted ERI, every tile read once per build
         jk_gbs = jk_bytes / (ms_jk_build * 1e-3) * 1e-9 if ms_jk_build > 0 else 0.0
         roofline = {
-            "kernel": "k_eri_grad_chunks<*> (16 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
+            "kernel": "k_eri_grad_chunks<*> (7 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
             "bound": "fp64", "bound_note": "FP64 CUDA-core pipe (neither HBM nor tensor cores bound this kernel: %s)" % (
                 "DRAM traffic %.2f GB per step" % (traffic * 1e-9) if traffic else "see profiles/"),
             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
@@ -245,7 +245,7 @@ def run_ours(args):
             "jk_kernel": {"kernel": "k_jk_cols", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
                           "frac": jk_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_build": ms_jk_build, "builds_per_step": builds,
                           "algorithmic_bytes_per_build": jk_bytes,
-                          "traffic": ex.get("k_jk_chunks", {}).get("dram_bytes_per_launch") if ex else None},
+                          "traffic": ex.get("k_jk_cols", {}).get("dram_bytes_per_launch") if ex else None},
         }
         h2d = int(lnalpha.nbytes + np.asarray(s.coef).nbytes + s.xyz.nbytes + 4 * (2 * s.nbasis + s.natoms) + s.atom.nbytes)
         d2h = int(8 * (1 + 2 * len(s.alpha) + 3 * s.nbasis) + 8 * (s.nbasis * s.nbasis + s.nbasis))
