@@ -35,6 +35,16 @@ static void fail(int code, const char* fmt, const char* a = "") {
   throw Fail{code};
 }
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) fail(-2, "CUDA error: %s", cudaGetErrorString(e_)); } while (0)
+// launch errors (bad configuration, attribute not granted) do not surface through the stream: poll them where a phase ends,
+// so that nothing stale is left for the caller's next CUDA call to trip over
+static void check_launches(const char* where) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+    fail(-2, "CUDA error after %s", buf);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Device-memory pool: freed blocks are kept (per device, by exact size) and handed out again, so that repeated
@@ -510,6 +520,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   launch_axpby(st, (int)nn, 1.0, T, 0.0, H);
   launch_axpby(st, (int)nn, 1.0, V, 1.0, H);                                  // Energy.py:137
   t_stats.ms_one_electron = t_1e.stop();
+  check_launches("setup / one-electron kernels");
 
   // SCF buffers
   double *L = ws.alloc<double>(nn), *wS = ws.alloc<double>(n), *X = ws.alloc<double>(nn), *t1 = ws.alloc<double>(nn),
@@ -587,6 +598,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   setup_jk_mode(P, opt);
   compute_eri_store(P);                                                        // Energy.py:136
   t_stats.ms_eri = t_eri.stop();
+  check_launches("ERI tile kernels");
 
   Timer t_scf(st);
   CU(cudaStreamWaitEvent(st, ev_side, 0));
@@ -633,6 +645,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   }
   t_stats.ms_scf = t_scf.stop();
   t_stats.scf_iterations = out.niter;
+  check_launches("SCF kernels");
 
   if (want_grad) {
     // ---- exact reverse sweep of the k iterations actually performed
@@ -685,6 +698,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     launch_gemm(st, false, false, n, n, n, L, n, t2, n, t1, n, 1.0, 0.0);
     launch_gemm(st, false, true, n, n, n, t1, n, L, n, Sbar, n, 1.0, 0.0);
     t_stats.ms_reverse = t_rev.stop();
+    check_launches("reverse-sweep kernels");
 
     Timer t_g(st);
     if (eri_grad_smem_bytes(P.kkmax) > 220 * 1024) fail(-1, "contraction too long for the ERI-gradient kernel's shared-memory accumulators");
@@ -705,6 +719,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     }
     t_fork.end(st);
     t_stats.ms_eri_grad = t_gk.stop();
+    check_launches("ERI-gradient kernels");
     launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
     if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);
     launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, ga, gc, gx);
@@ -728,6 +743,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     t_stats.n_tiles_skipped = (int64_t)sk;
   }
   CU(cudaStreamSynchronize(st));
+  check_launches("gradient assembly");
   t_stats.ms_jk = jk.ms();
   t_stats.ms_total = t_total.stop();
   t_stats.launches = launch_count();
@@ -865,6 +881,7 @@ static void run_batch(const dq_system* shape, int nmol, const double* atoms, con
       if (niter) niter[m0 + m] = hn[m];
     }
   }
+  check_launches("batched kernels");
   t_stats.n_quartets = (int64_t)qlist.size() * nmol;
   t_stats.n_prim_quartets = npq * nmol;
   t_stats.ms_total = t_total.stop();

@@ -632,8 +632,7 @@ void launch_batch_eri(cudaStream_t st, int cls, const BatchDev& b, const int2* q
 template <bool A, bool B, bool C, bool D>
 static void batch_grad_launch(cudaStream_t st, int blocks, size_t smem, const BatchDev& b, const int2* qlist, int nq, const double* terms,
                               const int* nterms, int max_scf, double* padj, double* pasum) {
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(kb_eri_grad<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  ensure_dynamic_smem(kb_eri_grad<A, B, C, D>, smem);
   kb_eri_grad<A, B, C, D><<<blocks, 128, smem, st>>>(b, qlist, nq, terms, nterms, max_scf, padj, pasum);
 }
 void launch_batch_eri_grad(cudaStream_t st, int cls, const BatchDev& b, const int2* qlist, int nq, const double* terms, const int* nterms,
@@ -659,8 +658,7 @@ int launch_batch_scf(cudaStream_t st, const BatchDev& b, const double* S, const 
   bool in_smem = batch_scf_smem_bytes(b.N, b.neri, true) <= 100 * 1024;
   const size_t smem = batch_scf_smem_bytes(b.N, b.neri, in_smem);
   if (smem > 220 * 1024) return -1;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(kb_scf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  ensure_dynamic_smem(kb_scf, smem);
   kb_scf<<<b.nmol, 128, smem, st>>>(b, S, H, eri, in_smem ? 1 : 0, max_scf, tol, want_grad, hist, Eelec, niter, conv, esteps, C, eps, terms,
                                     nterms, Hbar, Sbar);
   DQB_LAUNCHED();

@@ -1118,23 +1118,13 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_eri_tiles<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr = true;
-  }
+  ensure_dynamic_smem(k_eri_tiles<A, B, C, D>, 200 * 1024, true);
   k_eri_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
 }
 template <bool A, bool B, bool C, bool D>
 static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
                         int nterms, const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_eri_grad_chunks<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_eri_grad_chunks<A, B, C, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // 2 CTAs x ~105 KB
-    attr = true;
-  }
+  ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D>, 220 * 1024, true);   // 2 CTAs x ~105 KB
   k_eri_grad_chunks<A, B, C, D><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
 }
 
@@ -1179,13 +1169,11 @@ void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, in
                       const double* D, double* Jacc, double* Kacc) {
   if (nchunks <= 0) return;
   const size_t smem = ((size_t)16 * (s.N | 1) + 2 * 16 * 17 + 16) * sizeof(double) + 256 * 16;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(k_jk_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  ensure_dynamic_smem(k_jk_chunks, smem);
   static const bool old_kernel = getenv("DQ_JK_DIGEST") != nullptr;   // A/B switch: the per-tile digest kernel
   if (old_kernel) { k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED(); return; }
   const size_t smem2 = ((size_t)16 * (s.N | 1) + 16) * sizeof(double) + 256 * 16;
-  static size_t attr2 = 0;
-  if (smem2 > 48 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_jk_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); attr2 = smem2; }
+  ensure_dynamic_smem(k_jk_cols, smem2);
   k_jk_cols<<<nchunks, 256, smem2, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
 }
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
@@ -1228,15 +1216,13 @@ void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, do
   int* meta = (int*)base; base += (((size_t)batch * sizeof(int) + 255) / 256) * 256;
   unsigned short* tab = (unsigned short*)base;
   const size_t smem1 = (size_t)(ne * (ne + 1) / 2 + 2 * m) * sizeof(double) + (size_t)2 * m * sizeof(int);
-  static size_t attr1 = 0;
-  if (smem1 > 48 * 1024 && smem1 > attr1) { cudaFuncSetAttribute(k_jacobi_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1); attr1 = smem1; }
+  ensure_dynamic_smem(k_jacobi_packed, smem1);
   int threads = 1024;
   if (n <= 16) threads = 64; else if (n <= 32) threads = 128; else if (n <= 64) threads = 256; else if (n <= 128) threads = 512;
   k_jacobi_packed<<<batch, threads, smem1, st>>>(n, A, tab, log, meta, w, rank, kJacobiSweeps); DQ_LAUNCHED();
   int wpb = n < 4 ? n : 4;               // warps (rows) per CTA: many small CTAs spread the log reads over the SMs
   const size_t smem2 = (size_t)wpb * ne * sizeof(double);
-  static size_t attr2 = 0;
-  if (smem2 > 48 * 1024 && smem2 > attr2) { cudaFuncSetAttribute(k_jacobi_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); attr2 = smem2; }
+  ensure_dynamic_smem(k_jacobi_vectors, smem2);
   dim3 grid((n + wpb - 1) / wpb, batch);
   k_jacobi_vectors<<<grid, wpb * 32, smem2, st>>>(n, log, meta, rank, Vout, kJacobiSweeps); DQ_LAUNCHED();
 }

@@ -3,9 +3,29 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include <map>
+#include <utility>
+
 #include "dq_layout.h"
 
 namespace dq {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remember what has been granted per
+// (kernel ADDRESS, device) -- template instantiations of one kernel share a function type, so the type cannot be the key --
+// so that one process driving several GPUs (one host thread each) opts in on every one of them.
+template <class K>
+inline void ensure_dynamic_smem(K kernel, size_t bytes, bool prefer_shared_carveout = false) {
+  if (bytes <= 48 * 1024 && !prefer_shared_carveout) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static thread_local std::map<std::pair<const void*, int>, size_t> granted;
+  size_t& g = granted[{(const void*)kernel, dev}];
+  if (bytes > g) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (prefer_shared_carveout) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    g = bytes;
+  }
+}
 
 int upload_boys_constants();
 long long launch_count();
