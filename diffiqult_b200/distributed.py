@@ -25,10 +25,15 @@ def make_allreduce(group=None, on_device=True):
     import torch
     import torch.distributed as dist
     calls = {"n": 0, "doubles": 0}
+    views = {}      # (pointer, count) -> tensor view: the library's pooled buffers keep their addresses from call to call
 
     def _cb(ptr, count, user):
         if on_device:
-            t = torch.as_tensor(_CudaBuffer(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+            t = views.get((ptr, count))
+            if t is None:
+                t = torch.as_tensor(_CudaBuffer(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+                if len(views) < 64:
+                    views[(ptr, count)] = t
         else:
             buf = (C.c_double * count).from_address(ptr)
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
