@@ -543,10 +543,16 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     }
     launch_gemm(sx, true, false, n, n, n, X, n, F, n, t1, n, 1.0, 0.0);       // Energy.py:166 (the duplicated block
     launch_gemm(sx, false, false, n, n, n, t1, n, X, n, Fp, n, 1.0, 0.0);     //   :170-173 recomputes the same C)
-    // Energy.py:167-168.  Warm start: successive Fock matrices are close, so F' is first rotated into the previous
-    // iteration's eigenbasis (nearly diagonal -> Jacobi converges in 2-4 sweeps instead of ~9); U = U_prev V.
+    // Energy.py:167-168.  Warm start: successive Fock matrices are close.  Cluster solver: the previous eigenvectors are
+    // the starting basis (2-4 sweeps instead of 7).  Single-CTA solver: F' is first rotated into the previous eigenbasis
+    // (nearly diagonal -> 2-4 sweeps instead of ~9) and U = U_prev V.
     if (it == 0 || getenv("DQ_COLD_EIGH")) {
       launch_eigh(sx, n, 1, Fp, vwork, U, eps, ework);
+    } else if (eigh_cluster_applicable(n)) {
+      // cluster solver: the previous eigenvectors go in as the starting basis, the new ones come out directly
+      launch_symmetrize(sx, n, Fp);
+      launch_eigh_cluster(sx, n, 1, Fp, U, t3, eps, ework);
+      CU(cudaMemcpyAsync(U, t3, nn * sizeof(double), cudaMemcpyDeviceToDevice, sx));
     } else {
       launch_gemm(sx, true, false, n, n, n, U, n, Fp, n, t1, n, 1.0, 0.0);      // U_prev^T F'
       launch_gemm(sx, false, false, n, n, n, t1, n, U, n, t2, n, 1.0, 0.0);     // U_prev^T F' U_prev
@@ -594,6 +600,10 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   }
   CU(cudaEventRecord(ev_side, side));
 
+  // The cluster eigensolver (8 CTAs x 196 KB of shared memory) does not co-schedule well with the tile kernels: overlapped,
+  // the two cold solves (~4 ms) cost the ERI pass 13 ms; they run first instead.  The single-CTA solver (DQ_EIGH_PACKED)
+  // overlaps for free.
+  if (eigh_cluster_applicable(n) && !getenv("DQ_SIDE_OVERLAP")) CU(cudaStreamWaitEvent(st, ev_side, 0));
   Timer t_eri(st);
   setup_jk_mode(P, opt);
   compute_eri_store(P);                                                        // Energy.py:136

@@ -9,6 +9,7 @@
 //   k_eri_grad_chunks<class>        sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode, chunks of tiles sharing the ket
 //   k_pair_bwd                      pair-field adjoints -> exponents, coefficients, centres
 //   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -993,6 +994,243 @@ __global__ void __launch_bounds__(256) k_jacobi_vectors(int n, const double2* __
   for (int x = lane; x < n; x += 32) Vout[rank[x]] = v[x];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Symmetric eigensolver on a thread-block CLUSTER (48 <= n <= kJacobiPackedMax): one-sided (Hestenes) Jacobi.
+//   G = (A + sigma I) V,  V orthogonal (identity, or the previous SCF iteration's eigenvectors as a warm start);
+//   plane rotations of column pairs, applied to G and V alike, make the columns of G mutually orthogonal; then
+//   V^T (A + sigma I)^2 V is diagonal, i.e. V holds the eigenvectors (sigma = 1.5 max_i sum_j |a_ij| makes A + sigma I
+//   positive definite with condition number <= 5) and lambda_i = g_i . v_i - sigma.
+// A rotation touches only its two columns, so the columns are DISTRIBUTED: 16 blocks of w = ceil(n/16) columns, two
+// blocks (2 w columns of G and of V, column-major) in the shared memory of each of the 8 CTAs of the cluster.  Per round
+// a CTA orthogonalises every column of its top block against every column of its bottom block (w steps of w disjoint
+// pairs, one warp per pair: 3 dot products, 1 rotation), then the blocks move one position round the ring (round-robin
+// tournament over the 16 blocks, block 0 fixed) by writing them into the NEXT buffer of the neighbour CTA through
+// distributed shared memory; 15 rounds = every pair of blocks once = one sweep (pairs inside a block in round 0).
+// Against the single-CTA two-sided kernel above: the same ~223 steps per sweep, each ~8x shorter (8 SMs, no packed-index
+// arithmetic), and a warm start needs no rotation of A into the old eigenbasis and no back-multiplication.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kOsCluster = 8;
+constexpr int kOsThreads = 512;
+constexpr int kOsMinN = 48;
+
+// one warp: orthogonalise columns (gp, gq) and carry (vp, vq) along.  Every pair with |cos| > 1e-16 is rotated; the return
+// value says whether the cosine BEFORE the rotation exceeded 1e-10.  A sweep in which no pair did leaves residual cosines
+// of order cos^2 / (relative gap) <= 1e-20 / gap: the solver stops after it without a verification sweep.
+// The rotation is orthogonal to the last bit by construction (cs = (1+t^2)^-1/2, sn = cs t) whatever the accuracy of t,
+// which only sets the convergence rate: t is evaluated in single precision on operands scaled by a power of two.
+__device__ __forceinline__ int os_rotate(double* __restrict__ gp, double* __restrict__ gq, double* __restrict__ vp,
+                                         double* __restrict__ vq, int n, int lane) {
+  double x[8], y[8];                              // n <= 256: at most 8 rows per lane, kept for the update
+  double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = lane + 32 * i;
+    x[i] = r < n ? gp[r] : 0.0; y[i] = r < n ? gq[r] : 0.0;
+    a = fma(x[i], x[i], a); b = fma(y[i], y[i], b); g = fma(x[i], y[i], g);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); g += __shfl_xor_sync(0xffffffffu, g, o);
+  }
+  const double ab = a * b, g2 = g * g;
+  if (ab == 0.0 || g2 <= 1e-32 * ab) return 0;   // a padding column, or orthogonal to working precision
+  // tan(theta) = 2g / (d + sign(d) sqrt(d^2 + 4 g^2)), d = b - a; operands scaled by the power of two of the larger one
+  const double d = b - a, g2x = 2.0 * g;
+  const int e = (__double2hiint(fmax(fabs(d), fabs(g2x))) >> 20) & 0x7ff;
+  const double scale = __hiloint2double((2046 - e) << 20, 0);     // 2^-(e-1023)
+  const float df = (float)(d * scale), gf = (float)(g2x * scale);
+  const float hf = sqrtf(df * df + gf * gf);
+  const double t = (double)__fdividef(gf, df + copysignf(hf, df));
+  const double cs = rsqrt_(t * t + 1.0), sn = cs * t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = lane + 32 * i;
+    if (r < n) {
+      gp[r] = cs * x[i] - sn * y[i]; gq[r] = sn * x[i] + cs * y[i];
+      const double u = vp[r], v = vq[r];
+      vp[r] = cs * u - sn * v; vq[r] = sn * u + cs * v;
+    }
+  }
+  return g2 > 1e-20 * ab;
+}
+
+__global__ void __cluster_dims__(kOsCluster, 1, 1) __launch_bounds__(kOsThreads, 1)
+k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __restrict__ V0all, double* __restrict__ Voutall,
+                double* __restrict__ wall, double* __restrict__ lamall, int max_sweeps) {
+  extern __shared__ double sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  const int mat = blockIdx.x / kOsCluster;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t nn = (size_t)n * n;
+  const double* A = Aall + mat * nn;
+  const double* V0 = V0all ? V0all + mat * nn : nullptr;
+  const int blk = w * n;                       // doubles per block of G (or of V)
+  // two buffers of {G top, G bottom, V top, V bottom}
+  auto bufp = [&](int which) { return sm + (size_t)which * 4 * blk; };
+  __shared__ double s_red[kOsThreads / 32];
+  __shared__ double s_sigma;
+  __shared__ int s_rot;
+  __shared__ int s_cnt[2][kOsCluster];
+
+  // sigma = 1.5 * max_i sum_j |a_ij|  (every CTA computes the same value)
+  {
+    double mx = 0.0;
+    for (int r = tid; r < n; r += kOsThreads) {
+      double sum = 0.0;
+      for (int j = 0; j < n; ++j) sum += fabs(A[(size_t)j * n + r]);     // symmetric: column r read row-wise, coalesced
+      mx = fmax(mx, sum);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      double m2 = 0.0;
+      for (int x = 0; x < kOsThreads / 32; ++x) m2 = fmax(m2, s_red[x]);
+      s_sigma = m2 > 0.0 ? 1.5 * m2 : 1.0;
+      s_rot = 0;
+    }
+    __syncthreads();
+  }
+  const double sigma = s_sigma;
+  // initial blocks: top = block c, bottom = block c + 8; column j of block b is original column b*w + j (zero beyond n)
+  {
+    double* G = bufp(0);
+    double* V = bufp(0) + 2 * blk;
+    for (int x = tid; x < 2 * blk; x += kOsThreads) {
+      const int slot = x / blk, rem = x - slot * blk, j = rem / n, r = rem - j * n;
+      const int col = (slot == 0 ? c : c + kOsCluster) * w + j;
+      V[x] = col < n ? (V0 ? V0[(size_t)r * n + col] : (r == col ? 1.0 : 0.0)) : 0.0;
+    }
+    __syncthreads();
+    if (!V0) {
+      for (int x = tid; x < 2 * blk; x += kOsThreads) {
+        const int slot = x / blk, rem = x - slot * blk, j = rem / n, r = rem - j * n;
+        const int col = (slot == 0 ? c : c + kOsCluster) * w + j;
+        G[x] = col < n ? A[(size_t)col * n + r] + (r == col ? sigma : 0.0) : 0.0;
+      }
+    } else {
+      // G[:, j] = A V[:, j] + sigma V[:, j]: thread = (row r, half of the 2w columns), A read through its symmetry
+      const int half = tid / n, r = tid - half * n;            // needs 2 n <= 512 threads: n <= 256
+      if (half < 2) {
+        const int j0 = half * w;                               // columns j0 .. j0 + w - 1 of the 2w local columns
+        double acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double a = A[(size_t)k * n + r];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < w) acc[j] = fma(a, V[(j0 + j) * n + k], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j < w) G[(j0 + j) * n + r] = acc[j] + sigma * V[(j0 + j) * n + r];
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync();
+
+  int cur = 0;
+  const int m_in = (w + 1) / 2, np_in = 2 * m_in;        // round robin inside a block
+  // destinations of this CTA's blocks in the ring (block 0 = top of CTA 0 stays)
+  const int top_cta = c == 0 ? 0 : (c < kOsCluster - 1 ? c + 1 : kOsCluster - 1);
+  const int top_slot = (c == kOsCluster - 1) ? 1 : 0;
+  const int bot_cta = c == 0 ? 1 : c - 1;
+  const int bot_slot = c == 0 ? 0 : 1;
+  const int sweep_cap = max_sweeps < 0 ? -max_sweeps : max_sweeps;
+  for (int sweep = 0; sweep < sweep_cap; ++sweep) {
+    int rot = 0;
+    for (int rnd = 0; rnd < 2 * kOsCluster - 1; ++rnd) {
+      double* Gt = bufp(cur);
+      double* Gb = Gt + blk;
+      double* Vt = Gt + 2 * blk;
+      double* Vb = Gt + 3 * blk;
+      if (rnd == 0) {           // pairs inside each of the two resident blocks
+        for (int st = 0; st < np_in - 1; ++st) {
+          if (warp < 2 * m_in) {
+            const int which = warp / m_in, k = warp - which * m_in;
+            int p, q; rr_pair(st, k, np_in, &p, &q);
+            if (q < w) {
+              double* G = which ? Gb : Gt;
+              double* V = which ? Vb : Vt;
+              rot += os_rotate(G + p * n, G + q * n, V + p * n, V + q * n, n, lane);
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int st = 0; st < w; ++st) {      // every top column against every bottom column
+        if (warp < w) {
+          int q = warp + st; if (q >= w) q -= w;
+          rot += os_rotate(Gt + warp * n, Gb + q * n, Vt + warp * n, Vb + q * n, n, lane);
+        }
+        __syncthreads();
+      }
+      // move the blocks one position round the ring: into the other buffer of the destination CTA
+      {
+        double* dst_t = cluster.map_shared_rank(bufp(cur ^ 1), top_cta);
+        double* dst_b = cluster.map_shared_rank(bufp(cur ^ 1), bot_cta);
+        if ((blk & 1) == 0) {        // 16-byte remote stores (w * n even)
+          double2* d0 = (double2*)(dst_t + top_slot * blk); double2* d1 = (double2*)(dst_t + (2 + top_slot) * blk);
+          double2* d2 = (double2*)(dst_b + bot_slot * blk); double2* d3 = (double2*)(dst_b + (2 + bot_slot) * blk);
+          const double2 *s0 = (const double2*)Gt, *s1 = (const double2*)Vt, *s2 = (const double2*)Gb, *s3 = (const double2*)Vb;
+          for (int x = tid; x < blk / 2; x += kOsThreads) { d0[x] = s0[x]; d1[x] = s1[x]; d2[x] = s2[x]; d3[x] = s3[x]; }
+        } else {
+          for (int x = tid; x < blk; x += kOsThreads) {
+            dst_t[top_slot * blk + x] = Gt[x]; dst_t[(2 + top_slot) * blk + x] = Vt[x];
+            dst_b[bot_slot * blk + x] = Gb[x]; dst_b[(2 + bot_slot) * blk + x] = Vb[x];
+          }
+        }
+      }
+      if (rnd == 2 * kOsCluster - 2) {      // end of the sweep: publish this CTA's count of significant rotations
+        if (lane == 0 && rot) atomicAdd(&s_rot, rot);
+        __syncthreads();
+        if (tid < kOsCluster) cluster.map_shared_rank(&s_cnt[sweep & 1][0], tid)[c] = s_rot;
+      }
+      cluster.sync();
+      cur ^= 1;
+    }
+    int total = 0;
+#pragma unroll
+    for (int x = 0; x < kOsCluster; ++x) total += s_cnt[sweep & 1][x];
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    if (max_sweeps < 0 && c == 0 && tid == 0)
+      printf("[dq eigh] n %d sweep %d: %d pairs above 1e-10%s\n", n, sweep + 1, total, V0 ? " (warm)" : "");
+    if (total == 0) break;
+  }
+
+  // eigenvalues of the resident columns, global ranks, output in ascending order
+  double* G = bufp(cur);
+  double* V = bufp(cur) + 2 * blk;
+  double* lam = lamall + (size_t)mat * 2 * kOsCluster * w;
+  for (int j = warp; j < 2 * w; j += kOsThreads / 32) {
+    double gv = 0.0, gg = 0.0;
+    for (int r = lane; r < n; r += 32) { const double x = G[j * n + r]; gv += x * V[j * n + r]; gg += x * x; }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { gv += __shfl_xor_sync(0xffffffffu, gv, o); gg += __shfl_xor_sync(0xffffffffu, gg, o); }
+    if (lane == 0) lam[c * 2 * w + j] = gg > 0.0 ? gv - sigma : 1e300;      // padding columns sort last
+  }
+  __threadfence();
+  cluster.sync();
+  const int ntot = 2 * kOsCluster * w;
+  double* Vout = Voutall + mat * nn;
+  double* wout = wall + (size_t)mat * n;
+  for (int j = warp; j < 2 * w; j += kOsThreads / 32) {
+    const int me = c * 2 * w + j;
+    const double lj = __ldcg(lam + me);
+    if (lj >= 1e299) continue;
+    int rank = 0;
+    for (int x = lane; x < ntot; x += 32) { const double lx = __ldcg(lam + x); rank += (lx < lj) || (lx == lj && x < me); }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) wout[rank] = lj;
+    for (int r = lane; r < n; r += 32) Vout[(size_t)r * n + rank] = V[j * n + r];
+  }
+}
+
 // B[i,j] = A[i,j] * f(w[j]);  mode 0: w^-1/2
 __global__ void k_scale_cols_rsqrt(int n, const double* __restrict__ A, const double* __restrict__ w, double* __restrict__ B) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1198,9 +1436,32 @@ size_t eigh_workspace_bytes(int n, int batch) {
   b += (size_t)batch * kJacobiSweeps * (ne - 1 > 0 ? ne - 1 : 1) * m * sizeof(double2);   // rotation log
   b += (size_t)batch * n * sizeof(int) + (size_t)batch * sizeof(int) + 256;                // ranks, round counts
   b += (size_t)(m * (m - 1) / 2 + 1) * sizeof(unsigned short) + 256;                        // pair-of-pairs table
+  b += (size_t)batch * 2 * kOsCluster * ((n + 2 * kOsCluster - 1) / (2 * kOsCluster)) * sizeof(double) + 256;   // cluster solver: eigenvalues by position
   return b;
 }
+// cluster (one-sided) solver, optionally warm-started from V0 (n x n, orthogonal, e.g. the previous eigenvectors)
+bool eigh_cluster_applicable(int n) {
+  static const bool off = getenv("DQ_EIGH_PACKED") != nullptr;      // A/B switch: the single-CTA two-sided kernels
+  return !off && n >= kOsMinN && n <= kJacobiPackedMax;
+}
+void launch_eigh_cluster(cudaStream_t st, int n, int batch, const double* A, const double* V0, double* Vout, double* w, void* work) {
+  const int ne = n + (n & 1), m = ne / 2;
+  char* base = (char*)work;
+  base += (size_t)batch * kJacobiSweeps * (ne - 1) * m * sizeof(double2);
+  base += (size_t)batch * n * sizeof(int);
+  base += (((size_t)batch * sizeof(int) + 255) / 256) * 256;
+  base += (((size_t)(m * (m - 1) / 2 + 1) * sizeof(unsigned short) + 255) / 256) * 256;
+  double* lam = (double*)base;
+  const int wcol = (n + 2 * kOsCluster - 1) / (2 * kOsCluster);
+  const size_t smem = (size_t)8 * wcol * n * sizeof(double);
+  ensure_dynamic_smem(k_eigh_onesided, smem);
+  static const int sweeps = getenv("DQ_EIGH_DEBUG") ? -40 : 40;      // negative: print the per-sweep rotation counts
+  k_eigh_onesided<<<batch * kOsCluster, kOsThreads, smem, st>>>(n, wcol, A, V0, Vout, w, lam, sweeps); DQ_LAUNCHED();
+}
+bool eigh_cluster_applicable(int n);
+void launch_eigh_cluster(cudaStream_t st, int n, int batch, const double* A, const double* V0, double* Vout, double* w, void* work);
 void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w, void* work) {
+  if (work != nullptr && eigh_cluster_applicable(n)) { launch_eigh_cluster(st, n, batch, A, nullptr, Vout, w, work); return; }
   if (n > kJacobiPackedMax || n < 2 || work == nullptr) {
     const int m = (n + 1) / 2;
     const size_t smem = (size_t)2 * m * sizeof(double) + (size_t)2 * m * sizeof(int);

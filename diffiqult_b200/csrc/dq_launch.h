@@ -53,6 +53,9 @@ void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const d
 size_t eigh_workspace_bytes(int n, int batch);
 // `work`: eigh_workspace_bytes(n, batch) bytes of device memory (NULL: slow global-memory fallback)
 void launch_eigh(cudaStream_t st, int n, int batch, double* A, double* Vwork, double* Vout, double* w, void* work);
+// cluster one-sided Jacobi (48 <= n <= 236): A symmetric n x n (not modified), V0 = NULL or an orthogonal warm start
+bool eigh_cluster_applicable(int n);
+void launch_eigh_cluster(cudaStream_t st, int n, int batch, const double* A, const double* V0, double* Vout, double* w, void* work);
 void launch_scale_cols_rsqrt(cudaStream_t st, int n, const double* A, const double* w, double* B);
 void launch_fock_combine(cudaStream_t st, int n, const int* f_block, const double* H, const double* Jacc, const double* Kacc, double* F,
                          double* G);
