@@ -257,6 +257,10 @@ def run_ours(args):
                        "grid_spacing_bohr": args.spacing,
                        "n_basis": int(s.nbasis), "n_primitives": int(len(s.alpha)), "primitive_quartets": nq,
                        "scf_iterations": st["scf_iterations"], "converged": r["status"] == 0, "energy_hartree": r["E"],
+                       "gradient_quartets_with_exactly_zero_weight": "%.1f %% of this rank's contracted quartets: D and the adjoint "
+                       "Fock matrices are exactly zero between uncoupled far-apart monomers (the eigensolver keeps exact zeros), so "
+                       "these quartets add exactly 0 to the gradient and their primitive loops are skipped; the ERI pass itself "
+                       "evaluates everything" % (100.0 * st["n_grad_quartets_zero_weight"] / max(st["n_quartets"], 1)),
                        "jk_mode": ("integral-direct (tiles recomputed in every Fock build)" if st["jk_direct"] else
                                    "stored ERI tiles (%.2f GB per rank)" % (st["n_tiles"] * 2048 / 1e9)),
                        "l2": "ERI tile store larger than L2; every step recomputes everything from host inputs",

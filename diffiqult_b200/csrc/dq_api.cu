@@ -311,7 +311,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
   sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
-  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr;
+  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr;
   }
 
   if (!need_tiles) return;
@@ -416,14 +416,13 @@ static void setup_jk_mode(Prepared& P, const dq_options* opt) {
 static void compute_eri_store(Prepared& P) {
   if (P.direct) return;
   P.d_store = P.ws.alloc<double>((size_t)P.ntiles * kTile);
-  t_fork.init(P.ws.dev);
-  t_fork.begin(P.ws.st);
-  for (int c = 15, lane = 0; c >= 0; --c) {        // p-rich (long) classes first
+  // one stream: a value tile lives ~45 us, so the tails of the class launches are negligible, and concurrent class kernels
+  // made the pass time erratic (129-148 ms from run to run)
+  for (int c = 15; c >= 0; --c) {        // p-rich (long) classes first
     if (P.cls_start[c + 1] == P.cls_start[c]) continue;
-    launch_eri_tiles(t_fork.lane(lane++), c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
+    launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
                      P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
   }
-  t_fork.end(P.ws.st);
 }
 
 // unsort an N x N matrix (rows and/or columns) into the caller's ordering
@@ -718,6 +717,8 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     // gbuf = [g_alpha | g_coef(normalised) | g_xyz]  (one buffer: one allreduce)
     double* gbuf = ws.alloc<double>((size_t)2 * P.nprim + 3 * n, true);
     double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
+    unsigned long long* d_zero = ws.alloc<unsigned long long>(1, true);
+    P.sd.zero_weight = d_zero;
     Timer t_gk(st);
     t_fork.init(ws.dev);
     t_fork.begin(st);
@@ -736,6 +737,8 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     double* graw = ws.alloc<double>(P.nprim);
     launch_normalize_bwd(st, n, P.d_foff, P.d_ftype, P.d_alpha, P.d_craw, gc, ga, graw);
     if (P.log_alpha) launch_mul(st, P.nprim, ga, P.d_alpha, ga);                   // d/d ln(alpha) = alpha d/d alpha
+    unsigned long long h_zero = 0;
+    CU(cudaMemcpyAsync(&h_zero, d_zero, sizeof h_zero, cudaMemcpyDeviceToHost, st));
     std::vector<double> ha(P.nprim), hc(P.nprim), hx(3 * n);
     CU(cudaMemcpyAsync(ha.data(), ga, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hc.data(), graw, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -745,6 +748,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     if (g_xyz) for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) g_xyz[3 * P.f_orig[i] + c] = hx[3 * i + c];
     t_stats.ms_grad_other = t_g.stop() - t_stats.ms_eri_grad;
     t_stats.grad_terms = nterms;
+    t_stats.n_grad_quartets_zero_weight = (int64_t)h_zero;
   }
   if (P.sd.screen > 0.0 && !P.direct) {
     unsigned long long sk = 0;

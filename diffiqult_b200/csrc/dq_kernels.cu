@@ -574,6 +574,7 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
   const bool kvalid = kl < b2.nI && ll < b2.nJ;
   const long long off5k = b2.off / kPairFields * kAdjFields;
   double qcs = 0.0, qds = 0.0;
+  int nzero = 0;          // valid quartets of this thread whose two-particle weight is exactly zero (nothing to add)
   for (int k0 = 0; k0 < KKk; k0 += KC) {
     const int kn = KKk - k0 < KC ? KKk - k0 : KC;
     for (int x = 0; x < kn * kAdjFields; ++x) sacc[x * 256 + tid] = 0.0;
@@ -582,11 +583,12 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
       const Tile tl = tiles[ch.x + ti];
       if (tile_screened(s, tl)) continue;
       const BlockPair b1 = s.bp[tl.bp1];
+      const bool valid = kvalid && il < b1.nI && jl < b1.nJ;
       const int KKb = b1.KK;
       const int ia = b1.axI, ib = b1.axJ;
       const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
       double W = 0.0;
-      if (kvalid && il < b1.nI && jl < b1.nJ) {
+      if (valid) {
         const int i = b1.sI + il, j = b1.sJ + jl;
         for (int t = 0; t < nterms; ++t) {
           const double* A = At + t * nn;
@@ -596,7 +598,10 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
                       A[j * n + l] * B[i * n + k]);
         }
         W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (b1.bI == b1.bJ ? 0.5 : 1.0) * (b2.bI == b2.bJ ? 0.5 : 1.0);
+        if (k0 == 0 && W == 0.0) ++nzero;
       }
+      // a warp (2 bra lanes x 16 ket lanes) none of whose quartets carries weight has nothing to add for this tile
+      if (!__any_sync(0xffffffffu, W != 0.0)) continue;
       const long long off5b = b1.off / kPairFields * kAdjFields;
       const double* gbra = pd + b1.off * 16;
       double pas = 0.0, pbs = 0.0;
@@ -683,6 +688,11 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
       }
     }
     __syncthreads();
+  }
+  if (s.zero_weight) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+    if ((tid & 31) == 0 && nzero) atomicAdd(s.zero_weight, (unsigned long long)nzero);
   }
 }
 

@@ -46,6 +46,7 @@ struct SystemDev {
   const double* bp_kmax;   // [nbp]  max |K_ab| over the primitive-pair records of each block pair
   double screen;           // opt-in tile screening threshold (0: off)
   unsigned long long* skipped;   // counter of skipped tiles (screening on)
+  unsigned long long* zero_weight;   // counter of contracted quartets the gradient pass skipped because their weight is exactly 0
 };
 
 // Batch of molecules of ONE structure (dq_batch.cu).  Functions stay in the caller's order; function pairs x = (i <= j)

@@ -74,6 +74,9 @@ typedef struct dq_stats {
   int32_t jk_direct;       /* 1 if the Fock builds were integral-direct, 0 if they used the stored tiles */
   int64_t n_tiles_skipped; /* tiles skipped by the opt-in screening in the (last) ERI pass */
   double ms_jk;            /* sum of the J/K contraction kernels' times over all Fock builds (CUDA events, read once at the end) */
+  int64_t n_grad_quartets_zero_weight;  /* contracted quartets of this rank whose two-particle weight in the ERI-gradient pass is
+                            * EXACTLY 0.0 (both density-like factors vanish identically, e.g. between uncoupled far-apart
+                            * fragments): they add exactly nothing and their primitive loops are skipped */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):
