@@ -232,7 +232,9 @@ def run_ours(args):
                 "DRAM traffic %.2f GB per step" % (traffic * 1e-9) if traffic else "see profiles/"),
             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
             "achieved_basis": basis,
-            "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry); the loop's FMAs have one "
+                           "register operand - a DFMA with three distinct register operands, the normal case in the integral "
+                           "kernels, issues at 2/3 of this rate on B200 (scripts/microbench/fp64_pipe.cu, DESIGN.md section 3)",
             "fp64_pipe_active_ncu": ex["k_eri_grad_chunks"].get("pipe_fp64_active_frac") if ex else None,
             "algorithmic": {"flop_per_primitive_quartet": FLOP_GRAD, "achieved": alg_grad, "frac": alg_grad / peak.value,
                             "note": "SURVEY.md 8(d) count of the reference's formulas (2.7 Boys calls x ~100 flop dominate); this "

@@ -152,6 +152,9 @@ struct TilePlan {
   std::vector<Tile> gtiles;
   std::vector<int2> gchunks;
   int gchunk_cls_start[17];
+  std::vector<int2> gchunks32;  // the same order cut into chunks of <= 32 tiles (sparse-weight gradient kernel: one mask bit per tile)
+  int gchunk32_cls_start[17];
+  int2* d_gchunks32 = nullptr;
   Tile* d_tiles = nullptr;
   int2* d_chunks = nullptr;
   Tile* d_gtiles = nullptr;
@@ -161,6 +164,7 @@ struct TilePlan {
     if (d_chunks) cudaFree(d_chunks);
     if (d_gtiles) cudaFree(d_gtiles);
     if (d_gchunks) cudaFree(d_gchunks);
+    if (d_gchunks32) cudaFree(d_gchunks32);
   }
 };
 static thread_local std::shared_ptr<TilePlan> t_plan;
@@ -364,7 +368,19 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       }
     }
     tp->gchunk_cls_start[16] = (int)tp->gchunks.size();
+    for (int c = 0; c < 16; ++c) {
+      tp->gchunk32_cls_start[c] = (int)tp->gchunks32.size();
+      for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
+        int e = t + 1;
+        while (e < tp->cls_start[c + 1] && e - t < 32 && tp->gtiles[e].bp2 == tp->gtiles[t].bp2) ++e;
+        tp->gchunks32.push_back(make_int2(t, e - t));
+        t = e;
+      }
+    }
+    tp->gchunk32_cls_start[16] = (int)tp->gchunks32.size();
     if (!P.plan_only) {
+      CU(cudaMalloc(&tp->d_gchunks32, std::max<size_t>(tp->gchunks32.size(), 1) * sizeof(int2)));
+      CU(cudaMemcpyAsync(tp->d_gchunks32, tp->gchunks32.data(), tp->gchunks32.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
       CU(cudaMalloc(&tp->d_gtiles, std::max<size_t>(tp->gtiles.size(), 1) * sizeof(Tile)));
       CU(cudaMalloc(&tp->d_gchunks, std::max<size_t>(tp->gchunks.size(), 1) * sizeof(int2)));
       CU(cudaMemcpyAsync(tp->d_gtiles, tp->gtiles.data(), tp->gtiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
@@ -720,9 +736,32 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     unsigned long long* d_zero = ws.alloc<unsigned long long>(1, true);
     P.sd.zero_weight = d_zero;
     Timer t_gk(st);
+    // dense or sparse weights?  The density matrix of well separated fragments is exactly zero between them (the cluster
+    // eigensolver keeps exact zeros), and then most quartets carry no weight: the lane-independent kernel pays off.
+    bool sparse = false;
+    {
+      const char* force = getenv("DQ_GRAD_KERNEL");
+      if (force) sparse = force[0] == 's';
+      else {
+        int* d_nz = ws.alloc<int>(1);
+        int h_nz = 0;
+        launch_count_nonzero(st, (int)nn, hD[k - 1], d_nz);
+        CU(cudaMemcpyAsync(&h_nz, d_nz, sizeof h_nz, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        sparse = (double)h_nz < 0.25 * (double)nn;
+      }
+    }
+    t_stats.grad_kernel_sparse = sparse ? 1 : 0;
     t_fork.init(ws.dev);
     t_fork.begin(st);
     for (int c = 15, lane = 0; c >= 0; --c) {
+      if (sparse) {
+        const int nch = P.tp->gchunk32_cls_start[c + 1] - P.tp->gchunk32_cls_start[c];
+        if (nch <= 0) continue;
+        launch_eri_grad_sparse(t_fork.lane(lane++), c, P.tp->d_gtiles, P.tp->d_gchunks32 + P.tp->gchunk32_cls_start[c], nch, P.sd,
+                               P.d_pd, nterms, At, Bt, padj, pasum, P.kkmax);
+        continue;
+      }
       const int nch = P.tp->gchunk_cls_start[c + 1] - P.tp->gchunk_cls_start[c];
       if (nch <= 0) continue;
       launch_eri_grad_chunks(t_fork.lane(lane++), c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c], nch, P.sd, P.d_pd,

@@ -41,6 +41,10 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, int kkmax);
 void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
                             const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
+// sparse-weight variant (chunks of <= 32 tiles) and the nonzero count the host chooses by
+void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
+                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
+void launch_count_nonzero(cudaStream_t st, int n2, const double* A, int* out);
 size_t eri_grad_smem_bytes(int kkmax);
 void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
                            double* packed);

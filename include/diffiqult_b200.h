@@ -77,6 +77,8 @@ typedef struct dq_stats {
   int64_t n_grad_quartets_zero_weight;  /* contracted quartets of this rank whose two-particle weight in the ERI-gradient pass is
                             * EXACTLY 0.0 (both density-like factors vanish identically, e.g. between uncoupled far-apart
                             * fragments): they add exactly nothing and their primitive loops are skipped */
+  int32_t grad_kernel_sparse;   /* 1: the ERI-gradient pass used the lane-independent kernel for sparse weights (chosen when
+                                 * fewer than 25 % of the elements of the final density matrix are nonzero), 0: the dense one */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):
