@@ -628,3 +628,35 @@ def test_random_systems_vs_oracle(seed):
                 continue        # the stopping rule fired at a different iteration: E_k is not the same function there
             fd = (e_pm[0] - e_pm[1]) / (2 * h)
             assert abs(fd - g[idx]) < 5e-6 * max(1.0, np.abs(g).max()), (n, idx, fd, g[idx])
+
+
+def test_sparse_weight_gradient_kernel_equals_dense(monkeypatch):
+    """The lane-independent ERI-gradient kernel (chosen automatically when the density matrix is mostly exact zeros) forced
+    on systems with dense weights: same gradient as the tile-synchronous kernel, and both against the oracle; and the
+    automatic choice on two far-apart water monomers, whose density is exactly block diagonal."""
+    for name in ("ch2o", "h2o_sto3g", "ch4"):
+        s = sysmol(name)
+        args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+        monkeypatch.setenv("DQ_GRAD_KERNEL", "dense")
+        d = Energy.rhf_grad(*args, max_scf=100)
+        monkeypatch.setenv("DQ_GRAD_KERNEL", "sparse")
+        sp = Energy.rhf_grad(*args, max_scf=100)
+        assert d["stats"]["grad_kernel_sparse"] == 0 and sp["stats"]["grad_kernel_sparse"] == 1
+        for n in range(3):
+            assert np.abs(d["grad"][n] - sp["grad"][n]).max() < 1e-11 * max(1.0, np.abs(d["grad"][n]).max())
+    monkeypatch.delenv("DQ_GRAD_KERNEL")
+    # N = 56 >= 48: the cluster eigensolver, which keeps the exact zeros between the eight far-apart monomers
+    mol = synthetic.water_cluster(8, spacing=40.0)
+    s = System_mol(mol, basis_set_3G_STO, 80, "w8far")
+    args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+    r = Energy.rhf_grad(*args, max_scf=100)
+    assert r["status"] == 0 and r["stats"]["grad_kernel_sparse"] == 1
+    assert r["stats"]["n_grad_quartets_zero_weight"] > 0.3 * r["stats"]["n_quartets"]     # 37 % for 8 monomers, 80 % for 32
+    monkeypatch.setenv("DQ_GRAD_KERNEL", "dense")
+    d = Energy.rhf_grad(*args, max_scf=100)
+    assert d["stats"]["grad_kernel_sparse"] == 0 and abs(d["E"] - r["E"]) < 1e-11
+    for n in range(3):
+        assert np.abs(d["grad"][n] - r["grad"][n]).max() < 1e-11 * max(1.0, np.abs(d["grad"][n]).max())
+    # every monomer is a rigidly rotated copy plus jitter: the centre gradient of the whole cluster sums to ~0 per monomer
+    # only up to the jitter, but translational invariance of the TOTAL energy holds exactly for floating Gaussians + nuclei
+    # moved together; here only the Gaussians move, so no such identity applies - the dense kernel is the reference.
