@@ -152,7 +152,7 @@ struct TilePlan {
   std::vector<Tile> gtiles;
   std::vector<int2> gchunks;
   int gchunk_cls_start[17];
-  std::vector<int2> gchunks32;  // the same order cut into chunks of <= 32 tiles (sparse-weight gradient kernel: one mask bit per tile)
+  std::vector<int2> gchunks32;  // the same order cut into chunks of <= 20 tiles (sparse-weight gradient kernel: its work list is in shared memory)
   int gchunk32_cls_start[17];
   int2* d_gchunks32 = nullptr;
   Tile* d_tiles = nullptr;
@@ -372,7 +372,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       tp->gchunk32_cls_start[c] = (int)tp->gchunks32.size();
       for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
         int e = t + 1;
-        while (e < tp->cls_start[c + 1] && e - t < 32 && tp->gtiles[e].bp2 == tp->gtiles[t].bp2) ++e;
+        while (e < tp->cls_start[c + 1] && e - t < 20 && tp->gtiles[e].bp2 == tp->gtiles[t].bp2) ++e;     // kSparseChunk
         tp->gchunks32.push_back(make_int2(t, e - t));
         t = e;
       }

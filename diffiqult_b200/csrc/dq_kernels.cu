@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kGradKetChunk = 9;   // ket primitive pairs whose adjoint slots are resident at once
+constexpr int kSparseChunk = 20;   // tiles per chunk of the sparse-weight gradient kernel (its work list lives in shared memory)
 
 // ERI gradient: sum over the quartets of Wsym(ijkl) * d(ij|kl)/d(primitive-pair fields)
 //   Wsym = wtile * sum_terms [ 8 (A_ij B_kl + A_kl B_ij) - 2 (A_ik B_jl + A_jk B_il + A_il B_jk + A_jl B_ik) ]
@@ -698,12 +699,14 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
 
 // ---------------------------------------------------------------------------------------------
 // ERI gradient for SPARSE weights (selected by the host when the density matrix is mostly exact zeros: well separated
-// fragments).  Same chunks, same ket-adjoint slots, same primitive code as k_eri_grad_chunks, but the LANES of a warp walk
-// the tiles of the chunk independently: a lane first marks the tiles in which ITS quartet carries weight (a bit mask, up to
-// 32 tiles per chunk), then processes only those, each lane at its own tile.  A warp is busy for max-over-lanes(active
-// tiles) instead of for every tile in which any lane is active.  With lanes on different tiles the bra adjoints can no
-// longer be shuffle-reduced over the ket lanes: they go to global memory with one atomic each (cheap when the weights are
-// sparse, 16-way conflicts when they are dense - hence two kernels).
+// fragments, where ~80 % of the quartets carry exactly zero weight and the survivors sit in the same few lanes of every
+// tile).  Same chunks (tiles sharing the ket block pair) and the same primitive code as k_eri_grad_chunks, but the CTA
+// first COMPACTS its work: every thread evaluates the weight of its quartet in every tile of the chunk and appends the
+// (tile, lane) pairs with weight to a list in shared memory; then the 256 threads take list entries round robin, so all
+// lanes stay busy.  A thread is no longer tied to a ket lane or a bra lane, so nothing can be reduced across threads:
+// bra adjoints go to global memory with one atomic each as they are completed, ket adjoints accumulate in the thread's
+// private shared-memory slots during a quartet and are flushed with atomics after it (~90 atomics per contracted
+// quartet of 81 primitive quartets).  With dense weights the tile-synchronous kernel is the better one - hence two.
 // ---------------------------------------------------------------------------------------------
 template <bool LA, bool LB, bool LC, bool LD>
 __global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
@@ -711,132 +714,126 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
                   int nterms, const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
                   double* __restrict__ pasum) {
   extern __shared__ double sm[];
-  const int2 ch = chunks[blockIdx.x];
+  __shared__ int s_count;
+  const int2 ch = chunks[blockIdx.x];          // at most kSparseChunk tiles
   const int bp2 = tiles[ch.x].bp2;
   const BlockPair b2 = s.bp[bp2];
   const int tid = threadIdx.x;
-  const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
   const int KKk = b2.KK;
   double* sket = sm;
-  double* sacc = sket + KKk * kPairFields * 16;     // [(min(KKk, kGradKetChunk)*5 + 2)][256]
+  double* sacc = sket + KKk * kPairFields * 16;     // [min(KKk, kGradKetChunk)*5][256] per-thread scratch
   const int KC = KKk < kGradKetChunk ? KKk : kGradKetChunk;
+  unsigned short* items = (unsigned short*)(sacc + KC * kAdjFields * 256);            // [kSparseChunk * 256]
   {
     const double* gk = pd + b2.off * 16;
     for (int x = tid; x < KKk * kPairFields * 16; x += 256) sket[x] = gk[x];
   }
+  if (tid == 0) s_count = 0;
   const int n = s.N;
   const size_t nn = (size_t)n * n;
   const int ic = b2.axI, id = b2.axJ;
-  const int k = b2.sI + kl, l = b2.sJ + ll;
-  const bool kvalid = kl < b2.nI && ll < b2.nJ;
   const long long off5k = b2.off / kPairFields * kAdjFields;
   const double wket = b2.bI == b2.bJ ? 0.5 : 1.0;
-  // weight of this lane's quartet in tile tl (exactly as in k_eri_grad_chunks)
-  auto weight = [&](const Tile tl, const BlockPair& b1) -> double {
-    if (!(kvalid && il < b1.nI && jl < b1.nJ)) return 0.0;
-    const int i = b1.sI + il, j = b1.sJ + jl;
+  // weight of the quartet of lane t (= il*64 + jl*16 + kl*4 + ll) in tile tl, exactly as in k_eri_grad_chunks
+  auto weight = [&](const Tile tl, const BlockPair& b1, int t, bool* valid) -> double {
+    const int il = t >> 6, jl = (t >> 4) & 3, kl = (t >> 2) & 3, ll = t & 3;
+    *valid = kl < b2.nI && ll < b2.nJ && il < b1.nI && jl < b1.nJ;
+    if (!*valid) return 0.0;
+    const int i = b1.sI + il, j = b1.sJ + jl, k = b2.sI + kl, l = b2.sJ + ll;
     double W = 0.0;
-    for (int t = 0; t < nterms; ++t) {
-      const double* A = At + t * nn;
-      const double* B = Bt + t * nn;
+    for (int q = 0; q < nterms; ++q) {
+      const double* A = At + q * nn;
+      const double* B = Bt + q * nn;
       W += 8.0 * (A[i * n + j] * B[k * n + l] + A[k * n + l] * B[i * n + j]) -
            2.0 * (A[i * n + k] * B[j * n + l] + A[j * n + k] * B[i * n + l] + A[i * n + l] * B[j * n + k] +
                   A[j * n + l] * B[i * n + k]);
     }
     return W * ((tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (b1.bI == b1.bJ ? 0.5 : 1.0) * wket);
   };
-  double qcs = 0.0, qds = 0.0;
+  __syncthreads();
+  // phase 1: which (tile, lane) pairs carry weight
   int nzero = 0;
+  for (int ti = 0; ti < ch.y; ++ti) {
+    const Tile tl = tiles[ch.x + ti];
+    if (tile_screened(s, tl)) continue;
+    const BlockPair b1 = s.bp[tl.bp1];
+    bool valid;
+    const double W = weight(tl, b1, tid, &valid);
+    if (W != 0.0) items[atomicAdd(&s_count, 1)] = (unsigned short)((ti << 8) | tid);
+    else if (valid) ++nzero;
+  }
+  __syncthreads();
+  const int nitems = s_count;
+  // phase 2: list entries round robin
   for (int k0 = 0; k0 < KKk; k0 += KC) {
     const int kn = KKk - k0 < KC ? KKk - k0 : KC;
     for (int x = 0; x < kn * kAdjFields; ++x) sacc[x * 256 + tid] = 0.0;
-    __syncthreads();      // (first round: also publishes the staged ket records)
-    unsigned mask = 0u;   // tiles of the chunk (<= 32) in which this lane's quartet carries weight
-    for (int ti = 0; ti < ch.y; ++ti) {
+    for (int it = tid; it < nitems; it += 256) {
+      const int item = items[it], ti = item >> 8, t = item & 255;
+      const int bl = t >> 4, kt = t & 15;
       const Tile tl = tiles[ch.x + ti];
-      if (tile_screened(s, tl)) continue;
       const BlockPair b1 = s.bp[tl.bp1];
-      if (weight(tl, b1) != 0.0) mask |= 1u << ti;
-      else if (k0 == 0 && kvalid && il < b1.nI && jl < b1.nJ) ++nzero;
-    }
-    while (__any_sync(0xffffffffu, mask != 0u)) {
-      if (mask != 0u) {
-        const int ti = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        const Tile tl = tiles[ch.x + ti];
-        const BlockPair b1 = s.bp[tl.bp1];
-        const double W = weight(tl, b1);
-        const int KKb = b1.KK;
-        const int ia = b1.axI, ib = b1.axJ;
-        const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
-        const long long off5b = b1.off / kPairFields * kAdjFields;
-        const double* gbra = pd + b1.off * 16;
-        double pas = 0.0, pbs = 0.0;
-        for (int pb = 0; pb < KKb; ++pb) {
-          const double* brec = gbra + pb * kPairFields * 16;
-          PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
-          double bsl[4] = {0.0, 0.0, 0.0, 0.0};
-          const PairPrim bra = load_pair(brec, bl);
-          double bs[4] = {0.0, 0.0, 0.0, 0.0};
-          if (LA) bs[0] = brec[ia * 16 + bl];
-          if (LB) bs[1] = brec[ib * 16 + bl];
-          if (LC) bs[2] = brec[ic * 16 + bl];
-          if (LD) bs[3] = brec[id * 16 + bl];
-          for (int pk = 0; pk < kn; ++pk) {
-            const double* krec = sket + (k0 + pk) * kPairFields * 16;
-            const PairPrim ket = load_pair(krec, kt);
-            double ds[4] = {0.0, 0.0, 0.0, 0.0};
-            if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
-            if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
-            if (LC) ds[2] = bs[2] - krec[ic * 16 + kt];
-            if (LD) ds[3] = bs[3] - krec[id * 16 + kt];
-            QuartetAdj q;
-            prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
-            ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
-            if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }
-            if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
-            if (LC) { bsl[2] += q.ds[2]; qcs += q.e[2]; }
-            if (LD) { bsl[3] += q.ds[3]; qds += q.e[3]; }
-            double* a = sacc + (pk * kAdjFields) * 256 + tid;
-            a[0] -= q.dP[0]; a[256] -= q.dP[1]; a[512] -= q.dP[2]; a[768] += q.gk; a[1024] += q.Kk;
-            if (LA) a[ia * 256] -= q.ds[0];
-            if (LB) a[ib * 256] -= q.ds[1];
-            if (LC) a[ic * 256] += q.e[2] - q.ds[2];
-            if (LD) a[id * 256] += q.e[3] - q.ds[3];
-          }
-          if (LA) add3(ba.P, ia, bsl[0]);
-          if (LB) add3(ba.P, ib, bsl[1]);
-          if (LC) add3(ba.P, ic, bsl[2]);
-          if (LD) add3(ba.P, id, bsl[3]);
-          double* o = padj + (off5b + (long long)pb * kAdjFields) * 16 + bl;
-          if (ba.P[0] != 0.0) atomicAdd(o, ba.P[0]);
-          if (ba.P[1] != 0.0) atomicAdd(o + 16, ba.P[1]);
-          if (ba.P[2] != 0.0) atomicAdd(o + 32, ba.P[2]);
-          if (ba.g != 0.0) atomicAdd(o + 48, ba.g);
-          if (ba.K != 0.0) atomicAdd(o + 64, ba.K);
+      bool valid;
+      const double W = weight(tl, b1, t, &valid);
+      const int KKb = b1.KK;
+      const int ia = b1.axI, ib = b1.axJ;
+      const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+      const long long off5b = b1.off / kPairFields * kAdjFields;
+      const double* gbra = pd + b1.off * 16;
+      double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
+      for (int pb = 0; pb < KKb; ++pb) {
+        const double* brec = gbra + pb * kPairFields * 16;
+        PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
+        double bsl[4] = {0.0, 0.0, 0.0, 0.0};
+        const PairPrim bra = load_pair(brec, bl);
+        double bs[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LA) bs[0] = brec[ia * 16 + bl];
+        if (LB) bs[1] = brec[ib * 16 + bl];
+        if (LC) bs[2] = brec[ic * 16 + bl];
+        if (LD) bs[3] = brec[id * 16 + bl];
+        for (int pk = 0; pk < kn; ++pk) {
+          const double* krec = sket + (k0 + pk) * kPairFields * 16;
+          const PairPrim ket = load_pair(krec, kt);
+          double ds[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
+          if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
+          if (LC) ds[2] = bs[2] - krec[ic * 16 + kt];
+          if (LD) ds[3] = bs[3] - krec[id * 16 + kt];
+          QuartetAdj q;
+          prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
+          ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
+          if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }
+          if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
+          if (LC) { bsl[2] += q.ds[2]; qcs += q.e[2]; }
+          if (LD) { bsl[3] += q.ds[3]; qds += q.e[3]; }
+          double* a = sacc + (pk * kAdjFields) * 256 + tid;
+          a[0] -= q.dP[0]; a[256] -= q.dP[1]; a[512] -= q.dP[2]; a[768] += q.gk; a[1024] += q.Kk;
+          if (LA) a[ia * 256] -= q.ds[0];
+          if (LB) a[ib * 256] -= q.ds[1];
+          if (LC) a[ic * 256] += q.e[2] - q.ds[2];
+          if (LD) a[id * 256] += q.e[3] - q.ds[3];
         }
-        if (LA && pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas);
-        if (LB && pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs);
+        if (LA) add3(ba.P, ia, bsl[0]);
+        if (LB) add3(ba.P, ib, bsl[1]);
+        if (LC) add3(ba.P, ic, bsl[2]);
+        if (LD) add3(ba.P, id, bsl[3]);
+        double* o = padj + (off5b + (long long)pb * kAdjFields) * 16 + bl;
+        if (ba.P[0] != 0.0) atomicAdd(o, ba.P[0]);
+        if (ba.P[1] != 0.0) atomicAdd(o + 16, ba.P[1]);
+        if (ba.P[2] != 0.0) atomicAdd(o + 32, ba.P[2]);
+        if (ba.g != 0.0) atomicAdd(o + 48, ba.g);
+        if (ba.K != 0.0) atomicAdd(o + 64, ba.K);
       }
-    }
-    const bool last = k0 + kn >= KKk;
-    int nslots = kn * kAdjFields;
-    if (last) {
-      sacc[(nslots + 0) * 256 + tid] = qcs;
-      sacc[(nslots + 1) * 256 + tid] = qds;
-      nslots += 2;
-    }
-    __syncthreads();
-    for (int slot = tid >> 4; slot < nslots; slot += 16) {
-      double sum = 0.0;
-#pragma unroll
-      for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + kt];
-      if (sum != 0.0) {
-        if (slot < kn * kAdjFields) atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + slot) * 16 + kt, sum);
-        else atomicAdd(pasum + ((long long)bp2 * 2 + (slot - kn * kAdjFields)) * 16 + kt, sum);
+      // this quartet's ket adjoints: flush the private slots and clear them for the next list entry
+      for (int x = 0; x < kn * kAdjFields; ++x) {
+        const double v = sacc[x * 256 + tid];
+        if (v != 0.0) { atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + x) * 16 + kt, v); sacc[x * 256 + tid] = 0.0; }
       }
+      if (LA && pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas);
+      if (LB && pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs);
+      if (LC && qcs != 0.0) atomicAdd(pasum + ((long long)bp2 * 2 + 0) * 16 + kt, qcs);
+      if (LD && qds != 0.0) atomicAdd(pasum + ((long long)bp2 * 2 + 1) * 16 + kt, qds);
     }
-    __syncthreads();
   }
   if (s.zero_weight) {
 #pragma unroll
@@ -1561,7 +1558,7 @@ static void grad_sparse_launch(cudaStream_t st, const Tile* tiles, const int2* c
 void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
                             const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
   if (nchunks <= 0) return;
-  const size_t smem = eri_grad_smem_bytes(kkmax);
+  const size_t smem = eri_grad_smem_bytes(kkmax) - (size_t)2 * 256 * sizeof(double) + (size_t)kSparseChunk * 256 * sizeof(unsigned short);
 #define CALL(a, b, c, d) grad_sparse_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, nterms, At, Bt, padj, pasum, smem)
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
