@@ -213,42 +213,45 @@ def run_ours(args):
         alg_eri = npq * FLOP_VALUE / (ms_eri_kernel * 1e-3) * 1e-12
         # the ncu counts are data dependent: they hold for the default workload only
         ex = executed_counts() if (args.spacing == 24.0 and args.waters == 32 and args.screen <= 0) else None
+        gk = "k_eri_grad_sparse" if st["grad_kernel_sparse"] else "k_eri_grad_chunks"
+        if ex and gk not in ex:
+            ex = None
         if ex:
-            achieved = npq * ex["k_eri_grad_chunks"]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
+            achieved = npq * ex[gk]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
             ach_eri = npq * ex["k_eri_tiles"]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
             basis = ("EXECUTED FP64 flop per primitive quartet on this workload (ncu smsp__sass_thread_inst_executed_op_"
                      "{2*dfma,dmul,dadd}_pred_on summed over the 7 class launches, %s) x primitive quartets / live CUDA-event "
                      "time of those launches" % ex.get("source", "profiles/fp64_executed.json"))
-            traffic = ex["k_eri_grad_chunks"].get("dram_bytes_per_step")
         else:
-            achieved, ach_eri, traffic = alg_grad, alg_eri, None
+            achieved, ach_eri = alg_grad, alg_eri
             basis = "ALGORITHMIC flop (SURVEY.md 8d) - profiles/fp64_executed.json absent"
         hbm_peak, hbm_src = measured_hbm_peak()
         jk_bytes = st["n_tiles"] * 2048.0                # 8 B per stored contracted ERI, every tile read once per build
         jk_gbs = jk_bytes / (ms_jk_build * 1e-3) * 1e-9 if ms_jk_build > 0 else 0.0
-        roofline = {
-            "kernel": "k_eri_grad_chunks<*> (7 class launches per step, %.0f %% of the step)" % (100 * ms_grad_kernel / (dev_ms / K)),
-            "bound": "fp64", "bound_note": "FP64 CUDA-core pipe (neither HBM nor tensor cores bound this kernel: %s)" % (
-                "DRAM traffic %.2f GB per step" % (traffic * 1e-9) if traffic else "see profiles/"),
-            "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
-            "achieved_basis": basis,
-            "peak_source": "measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry); the loop's FMAs have one "
-                           "register operand - a DFMA with three distinct register operands, the normal case in the integral "
-                           "kernels, issues at 2/3 of this rate on B200 (scripts/microbench/fp64_pipe.cu, DESIGN.md section 3)",
-            "fp64_pipe_active_ncu": ex["k_eri_grad_chunks"].get("pipe_fp64_active_frac") if ex else None,
-            "algorithmic": {"flop_per_primitive_quartet": FLOP_GRAD, "achieved": alg_grad, "frac": alg_grad / peak.value,
-                            "note": "SURVEY.md 8(d) count of the reference's formulas (2.7 Boys calls x ~100 flop dominate); this "
-                                    "geometry is almost entirely in the t >= 50 regime where the reference's continued fraction "
-                                    "equals its closed form to the last bit, so far fewer flop are executed: frac > 1 here is not "
-                                    "a hardware statement, `frac` above is"},
-            "eri_value_kernel": {"kernel": "k_eri_tiles<*>", "achieved": ach_eri, "frac": ach_eri / peak.value,
-                                 "algorithmic_achieved": alg_eri,
-                                 "fp64_pipe_active_ncu": ex["k_eri_tiles"].get("pipe_fp64_active_frac") if ex else None},
-            "jk_kernel": {"kernel": "k_jk_cols", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": jk_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_build": ms_jk_build, "builds_per_step": builds,
-                          "algorithmic_bytes_per_build": jk_bytes,
-                          "traffic": ex.get("k_jk_cols", {}).get("dram_bytes_per_launch") if ex else None},
-        }
+        step_ms = dev_ms / K
+        peak_src = ("measured live: dq_fp64_peak FMA loop (MEASURED_PEAKS.json has no FP64 entry); the loop's FMAs have one "
+                    "register operand - a DFMA with three distinct register operands, the normal case in the integral "
+                    "kernels, issues at 2/3 of this rate on B200 (scripts/microbench/fp64_pipe.cu, DESIGN.md section 3)")
+        alg_note = ("SURVEY.md 8(d) count of the reference's formulas (2.7 Boys calls x ~100 flop dominate); this geometry is "
+                    "almost entirely in the t >= 50 regime where the reference's continued fraction equals its closed form to the "
+                    "last bit, so far fewer flop are executed: frac > 1 here is not a hardware statement, `frac` is")
+
+        def tile_kernel(name, ms, ach, alg, alg_flop, key):
+            return {"kernel": "%s<*> (7 class launches per step, %.0f %% of the step)" % (name, 100 * ms / step_ms),
+                    "bound": "fp64", "bound_note": "FP64 CUDA-core pipe: neither HBM nor the tensor cores bound this kernel",
+                    "ms_per_step": ms, "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
+                    "traffic": ex[key].get("dram_bytes_per_step") if ex else None, "achieved_basis": basis, "peak_source": peak_src,
+                    "fp64_pipe_active_ncu": ex[key].get("pipe_fp64_active_frac") if ex else None,
+                    "algorithmic": {"flop_per_primitive_quartet": alg_flop, "achieved": alg, "frac": alg / peak.value, "note": alg_note}}
+        k_val = tile_kernel("k_eri_tiles", ms_eri_kernel, ach_eri, alg_eri, FLOP_VALUE, "k_eri_tiles")
+        k_grad = tile_kernel(gk, ms_grad_kernel, achieved, alg_grad, FLOP_GRAD, gk)
+        # the dominant kernel family of the step leads; the other tile kernel and the HBM-bound J/K kernel follow
+        roofline = dict(k_val if ms_eri_kernel >= ms_grad_kernel else k_grad)
+        roofline["other_tile_kernel"] = k_grad if ms_eri_kernel >= ms_grad_kernel else k_val
+        roofline["jk_kernel"] = {"kernel": "k_jk_cols", "bound": "hbm", "achieved": jk_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": jk_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_build": ms_jk_build,
+                                 "builds_per_step": builds, "algorithmic_bytes_per_build": jk_bytes,
+                                 "traffic": ex.get("k_jk_cols", {}).get("dram_bytes_per_launch") if ex else None}
         h2d = int(lnalpha.nbytes + np.asarray(s.coef).nbytes + s.xyz.nbytes + 4 * (2 * s.nbasis + s.natoms) + s.atom.nbytes)
         d2h = int(8 * (1 + 2 * len(s.alpha) + 3 * s.nbasis) + 8 * (s.nbasis * s.nbasis + s.nbasis))
         line = {
