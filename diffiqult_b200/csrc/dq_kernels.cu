@@ -1617,7 +1617,7 @@ size_t eigh_workspace_bytes(int n, int batch) {
   b += (size_t)batch * kJacobiSweeps * (ne - 1 > 0 ? ne - 1 : 1) * m * sizeof(double2);   // rotation log
   b += (size_t)batch * n * sizeof(int) + (size_t)batch * sizeof(int) + 256;                // ranks, round counts
   b += (size_t)(m * (m - 1) / 2 + 1) * sizeof(unsigned short) + 256;                        // pair-of-pairs table
-  b += (size_t)batch * 2 * kOsCluster * ((n + 2 * kOsCluster - 1) / (2 * kOsCluster)) * sizeof(double) + 256;   // cluster solver: eigenvalues by position
+  b += (size_t)batch * 2 * kOsCluster * ((n + 2 * kOsCluster - 1) / (2 * kOsCluster)) * sizeof(double) + 512;   // cluster solver: eigenvalues by position
   return b;
 }
 // cluster (one-sided) solver, optionally warm-started from V0 (n x n, orthogonal, e.g. the previous eigenvectors)
@@ -1632,6 +1632,7 @@ void launch_eigh_cluster(cudaStream_t st, int n, int batch, const double* A, con
   base += (size_t)batch * n * sizeof(int);
   base += (((size_t)batch * sizeof(int) + 255) / 256) * 256;
   base += (((size_t)(m * (m - 1) / 2 + 1) * sizeof(unsigned short) + 255) / 256) * 256;
+  base = (char*)(((size_t)base + 255) / 256 * 256);          // (the int arrays above leave it 4-byte aligned for odd n)
   double* lam = (double*)base;
   const int wcol = (n + 2 * kOsCluster - 1) / (2 * kOsCluster);
   const size_t smem = (size_t)8 * wcol * n * sizeof(double);
