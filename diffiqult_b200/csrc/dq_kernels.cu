@@ -1182,20 +1182,22 @@ constexpr int kOsMinN = 48;
 // of order cos^2 / (relative gap) <= 1e-20 / gap: the solver stops after it without a verification sweep.
 // The rotation is orthogonal to the last bit by construction (cs = (1+t^2)^-1/2, sn = cs t) whatever the accuracy of t,
 // which only sets the convergence rate: t is evaluated in single precision on operands scaled by a power of two.
+// |g_p|^2 and |g_q|^2 are not recomputed per pair: every column carries its squared norm (na, nb: shared memory, recomputed
+// exactly once per sweep, updated by the exact rotation identities in between), so a pair costs ONE dot product and ONE
+// shuffle reduction.  The norms only enter the skip test and the (single-precision) rotation angle.
 __device__ __forceinline__ int os_rotate(double* __restrict__ gp, double* __restrict__ gq, double* __restrict__ vp,
-                                         double* __restrict__ vq, int n, int lane) {
+                                         double* __restrict__ vq, double* na, double* nb, int n, int lane) {
   double x[8], y[8];                              // n <= 256: at most 8 rows per lane, kept for the update
-  double a = 0.0, b = 0.0, g = 0.0;
+  double g = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = lane + 32 * i;
     x[i] = r < n ? gp[r] : 0.0; y[i] = r < n ? gq[r] : 0.0;
-    a = fma(x[i], x[i], a); b = fma(y[i], y[i], b); g = fma(x[i], y[i], g);
+    g = fma(x[i], y[i], g);
   }
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); g += __shfl_xor_sync(0xffffffffu, g, o);
-  }
+  for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  const double a = *na, b = *nb;
   const double ab = a * b, g2 = g * g;
   if (ab == 0.0 || g2 <= 1e-32 * ab) return 0;   // a padding column, or orthogonal to working precision
   // tan(theta) = 2g / (d + sign(d) sqrt(d^2 + 4 g^2)), d = b - a; operands scaled by the power of two of the larger one
@@ -1215,7 +1217,22 @@ __device__ __forceinline__ int os_rotate(double* __restrict__ gp, double* __rest
       vp[r] = cs * u - sn * v; vq[r] = sn * u + cs * v;
     }
   }
+  __syncwarp();
+  if (lane == 0) {       // |c gp - s gq|^2 and |s gp + c gq|^2
+    const double cc = cs * cs, ss = sn * sn, x2 = 2.0 * cs * sn * g;
+    *na = cc * a - x2 + ss * b;
+    *nb = ss * a + x2 + cc * b;
+  }
   return g2 > 1e-20 * ab;
+}
+
+// exact squared norm of one column (one warp)
+__device__ __forceinline__ double os_norm2(const double* __restrict__ gcol, int n, int lane) {
+  double a = 0.0;
+  for (int r = lane; r < n; r += 32) a = fma(gcol[r], gcol[r], a);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
 }
 
 __global__ void __cluster_dims__(kOsCluster, 1, 1) __launch_bounds__(kOsThreads, 1)
@@ -1236,6 +1253,7 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
   __shared__ double s_sigma;
   __shared__ int s_rot;
   __shared__ int s_cnt[2][kOsCluster];
+  __shared__ double s_nrm[2][2][16];      // [buffer][top / bottom][column]: squared norms of the resident columns of G
 
   // sigma = 1.5 * max_i sum_j |a_ij|  (every CTA computes the same value)
   {
@@ -1310,7 +1328,14 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
       double* Gb = Gt + blk;
       double* Vt = Gt + 2 * blk;
       double* Vb = Gt + 3 * blk;
-      if (rnd == 0) {           // pairs inside each of the two resident blocks
+      double* nt_ = s_nrm[cur][0];
+      double* nb_ = s_nrm[cur][1];
+      if (rnd == 0) {           // once per sweep: exact norms, then the pairs inside each of the two resident blocks
+        for (int j = warp; j < 2 * w; j += kOsThreads / 32) {
+          const double v = os_norm2((j < w ? Gt : Gb) + (j < w ? j : j - w) * n, n, lane);
+          if (lane == 0) s_nrm[cur][j < w ? 0 : 1][j < w ? j : j - w] = v;
+        }
+        __syncthreads();
         for (int st = 0; st < np_in - 1; ++st) {
           if (warp < 2 * m_in) {
             const int which = warp / m_in, k = warp - which * m_in;
@@ -1318,7 +1343,8 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
             if (q < w) {
               double* G = which ? Gb : Gt;
               double* V = which ? Vb : Vt;
-              rot += os_rotate(G + p * n, G + q * n, V + p * n, V + q * n, n, lane);
+              double* nr = which ? nb_ : nt_;
+              rot += os_rotate(G + p * n, G + q * n, V + p * n, V + q * n, nr + p, nr + q, n, lane);
             }
           }
           __syncthreads();
@@ -1327,7 +1353,7 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
       for (int st = 0; st < w; ++st) {      // every top column against every bottom column
         if (warp < w) {
           int q = warp + st; if (q >= w) q -= w;
-          rot += os_rotate(Gt + warp * n, Gb + q * n, Vt + warp * n, Vb + q * n, n, lane);
+          rot += os_rotate(Gt + warp * n, Gb + q * n, Vt + warp * n, Vb + q * n, nt_ + warp, nb_ + q, n, lane);
         }
         __syncthreads();
       }
@@ -1346,6 +1372,10 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
             dst_b[bot_slot * blk + x] = Gb[x]; dst_b[(2 + bot_slot) * blk + x] = Vb[x];
           }
         }
+      }
+      if (tid < w) {            // the norms travel with their columns
+        cluster.map_shared_rank(&s_nrm[cur ^ 1][top_slot][0], top_cta)[tid] = nt_[tid];
+        cluster.map_shared_rank(&s_nrm[cur ^ 1][bot_slot][0], bot_cta)[tid] = nb_[tid];
       }
       if (rnd == 2 * kOsCluster - 2) {      // end of the sweep: publish this CTA's count of significant rotations
         if (lane == 0 && rot) atomicAdd(&s_rot, rot);
