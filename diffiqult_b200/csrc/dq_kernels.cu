@@ -1226,6 +1226,52 @@ __device__ __forceinline__ int os_rotate(double* __restrict__ gp, double* __rest
   return g2 > 1e-20 * ab;
 }
 
+// the same with the TOP column (G and V) resident in the caller's registers for a whole round: only the bottom column moves
+// through shared memory
+__device__ __forceinline__ int os_rotate_top(double (&x)[8], double (&u)[8], double* __restrict__ gq, double* __restrict__ vq,
+                                             double* na, double* nb, int n, int lane) {
+  double y[8];
+  double g = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = lane + 32 * i;
+    y[i] = r < n ? gq[r] : 0.0;
+    g = fma(x[i], y[i], g);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  const double a = *na, b = *nb;
+  const double ab = a * b, g2 = g * g;
+  if (ab == 0.0 || g2 <= 1e-32 * ab) return 0;
+  const double d = b - a, g2x = 2.0 * g;
+  const int e = (__double2hiint(fmax(fabs(d), fabs(g2x))) >> 20) & 0x7ff;
+  const double scale = __hiloint2double((2046 - e) << 20, 0);
+  const float df = (float)(d * scale), gf = (float)(g2x * scale);
+  const float hf = sqrtf(df * df + gf * gf);
+  const double t = (double)__fdividef(gf, df + copysignf(hf, df));
+  const double cs = rsqrt_(t * t + 1.0), sn = cs * t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = lane + 32 * i;
+    if (r < n) {
+      const double xn = cs * x[i] - sn * y[i];
+      gq[r] = sn * x[i] + cs * y[i];
+      x[i] = xn;
+      const double v = vq[r];
+      const double un = cs * u[i] - sn * v;
+      vq[r] = sn * u[i] + cs * v;
+      u[i] = un;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const double cc = cs * cs, ss = sn * sn, x2 = 2.0 * cs * sn * g;
+    *na = cc * a - x2 + ss * b;
+    *nb = ss * a + x2 + cc * b;
+  }
+  return g2 > 1e-20 * ab;
+}
+
 // exact squared norm of one column (one warp)
 __device__ __forceinline__ double os_norm2(const double* __restrict__ gcol, int n, int lane) {
   double a = 0.0;
@@ -1350,10 +1396,28 @@ k_eigh_onesided(int n, int w, const double* __restrict__ Aall, const double* __r
           __syncthreads();
         }
       }
-      for (int st = 0; st < w; ++st) {      // every top column against every bottom column
+      {                                     // every top column against every bottom column; warp i keeps top column i in registers
+        double xt[8], ut[8];
         if (warp < w) {
-          int q = warp + st; if (q >= w) q -= w;
-          rot += os_rotate(Gt + warp * n, Gb + q * n, Vt + warp * n, Vb + q * n, nt_ + warp, nb_ + q, n, lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = lane + 32 * i;
+            xt[i] = r < n ? Gt[warp * n + r] : 0.0; ut[i] = r < n ? Vt[warp * n + r] : 0.0;
+          }
+        }
+        for (int st = 0; st < w; ++st) {
+          if (warp < w) {
+            int q = warp + st; if (q >= w) q -= w;
+            rot += os_rotate_top(xt, ut, Gb + q * n, Vb + q * n, nt_ + warp, nb_ + q, n, lane);
+          }
+          __syncthreads();
+        }
+        if (warp < w) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = lane + 32 * i;
+            if (r < n) { Gt[warp * n + r] = xt[i]; Vt[warp * n + r] = ut[i]; }
+          }
         }
         __syncthreads();
       }
