@@ -128,7 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = REF_SAMPLE_WATERS
+    sample = args.ref_waters
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, e, cores = cpu_reference_step(sample)
@@ -298,6 +298,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--waters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-waters", type=int, default=REF_SAMPLE_WATERS, help="--impl reference: monomers in the bounded CPU sample")
     ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])
     ap.add_argument("--spacing", type=float, default=24.0, help="grid spacing of the water cluster in bohr (default 24: the "
                     "densest grid on which the reference's plain Roothaan iteration converges; smaller values are kernel studies)")

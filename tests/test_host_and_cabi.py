@@ -184,3 +184,19 @@ def test_batch_host_logic():
     if _capi.lib().dq_device_count() == 0:
         with pytest.raises(_capi.DiffiqultB200Error, match="no CUDA device"):
             batch.rhf_grad_batch_fused(ch4, max_scf=5)
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference algorithm on the host cores, a bounded sample): one JSON
+    line with the contract's keys, no GPU needed."""
+    import json
+    import subprocess
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-waters", "1"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "eri_plus_gradient_primitive_quartets_per_s"
+    assert line["value"] > 0 and line["unit"] == "primitive quartets/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("(H2O)_32") and line["n_gpus"] == 1 and line["steps"] == 1
