@@ -262,6 +262,10 @@ def run_ours(args):
                        "grid_spacing_bohr": args.spacing,
                        "n_basis": int(s.nbasis), "n_primitives": int(len(s.alpha)), "primitive_quartets": nq,
                        "scf_iterations": st["scf_iterations"], "converged": r["status"] == 0, "energy_hartree": r["E"],
+                       "primitive_pairs_underflowed": "%.1f %% of the primitive-pair prefactors exp(-ab|AB|^2/(a+b)) underflow to exactly 0 "
+                       "in double precision (monomers 24+ bohr apart); primitive quartets containing one are exact zeros, value "
+                       "and derivatives, and are not expanded (bit-identical results; DQ_NO_ZERO_SKIP=1 expands them)" % (
+                           100.0 * st["n_prim_pairs_underflowed"] / max(st["n_prim_pairs"], 1)),
                        "gradient_quartets_with_exactly_zero_weight": "%.1f %% of this rank's contracted quartets: D and the adjoint "
                        "Fock matrices are exactly zero between uncoupled far-apart monomers (the eigensolver keeps exact zeros), so "
                        "these quartets add exactly 0 to the gradient and their primitive loops are skipped; the ERI pass itself "

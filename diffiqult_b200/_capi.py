@@ -34,7 +34,8 @@ class dq_stats(C.Structure):
                 ("ms_grad_other", C.c_double), ("ms_total", C.c_double), ("launches", C.c_int64), ("n_tiles", C.c_int64),
                 ("n_quartets", C.c_int64), ("n_prim_quartets", C.c_int64), ("scf_iterations", C.c_int32),
                 ("fock_builds", C.c_int32), ("grad_terms", C.c_int32), ("jk_direct", C.c_int32), ("n_tiles_skipped", C.c_int64),
-                ("ms_jk", C.c_double), ("n_grad_quartets_zero_weight", C.c_int64), ("grad_kernel_sparse", C.c_int32)]
+                ("ms_jk", C.c_double), ("n_grad_quartets_zero_weight", C.c_int64), ("n_prim_pairs", C.c_int64),
+                ("n_prim_pairs_underflowed", C.c_int64), ("grad_kernel_sparse", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

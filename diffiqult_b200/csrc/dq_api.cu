@@ -189,6 +189,7 @@ struct Prepared {
   size_t ntiles = 0;
   double* d_store = nullptr;
   unsigned long long* d_skipped = nullptr;
+  unsigned long long* d_underflowed = nullptr;
   bool direct = false;          // integral-direct Fock builds: tiles recomputed batch by batch into d_batch
   double* d_batch = nullptr; size_t batch_tiles = 0;
   bool log_alpha = false;
@@ -315,7 +316,8 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
   sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
-  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr;
+  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr; sd.underflowed = nullptr;
+  sd.zero_skip = getenv("DQ_NO_ZERO_SKIP") ? 0 : 1;
   }
 
   if (!need_tiles) return;
@@ -405,7 +407,10 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   P.sd.bp_kmax = d_kmax;
   P.sd.screen = (opt && opt->screen_threshold > 0.0) ? opt->screen_threshold : 0.0;
   P.sd.skipped = P.d_skipped;
+  P.d_underflowed = ws.alloc<unsigned long long>(1, true);
+  P.sd.underflowed = P.d_underflowed;
   launch_pairs(st, P.sd, P.d_pd, d_kmax);
+  P.sd.underflowed = nullptr;
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
@@ -794,6 +799,15 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     CU(cudaMemcpyAsync(&sk, P.d_skipped, sizeof sk, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     t_stats.n_tiles_skipped = (int64_t)sk;
+  }
+  {
+    unsigned long long uf = 0;
+    CU(cudaMemcpyAsync(&uf, P.d_underflowed, sizeof uf, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t_stats.n_prim_pairs_underflowed = (int64_t)uf;
+    long long tot = 0;
+    for (const BlockPair& b : P.bps) tot += (long long)b.KK * b.nI * b.nJ;
+    t_stats.n_prim_pairs = tot;
   }
   CU(cudaStreamSynchronize(st));
   check_launches("gradient assembly");

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(128) k_pairs(SystemDev s, double* __restrict__
     double* o = pd + ((b.off + (long long)pp * kPairFields) * 16 + lane);
     o[0] = r.P[0]; o[16] = r.P[1]; o[32] = r.P[2]; o[48] = r.g; o[64] = r.ginv; o[80] = r.K; o[96] = r.pa; o[112] = r.pb;
     kmax = fmax(kmax, fabs(r.K));
+    if (valid && s.underflowed && pair_underflowed(r.K)) atomicAdd(s.underflowed, 1ULL);
   }
   // non-negative doubles order like their bit patterns (bp_kmax is zeroed by the launcher)
   if (kmax > 0.0) atomicMax((unsigned long long*)(bp_kmax + blockIdx.x), (unsigned long long)__double_as_longlong(kmax));
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
     for (int pb = 0; pb < c.b1.KK; ++pb) {
       const double* brec = sbra + pb * kPairFields * 16;
       const PairPrim bra = load_pair(brec, c.bl);
+      if (s.zero_skip && bra.K == 0.0) continue;      // exactly zero prefactor: the 9 quartets below are exact zeros
       // the components of P along the axes of the p functions come straight from the staged records at a CTA-uniform
       // offset: no per-primitive select
       double bs[4] = {0.0, 0.0, 0.0, 0.0};
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
       for (int pk = 0; pk < c.b2.KK; ++pk) {
         const double* krec = sket + pk * kPairFields * 16;
         const PairPrim ket = load_pair(krec, c.kt);
+        if (s.zero_skip && ket.K == 0.0) continue;
         double ds[4] = {0.0, 0.0, 0.0, 0.0};
         if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
         if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
@@ -612,8 +615,8 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         // adjoints of bra.P along the axes of the four p functions, summed over the ket primitives and folded into ba.P
         // once per bra primitive (the axis is CTA-uniform: no select inside the ket loop)
         double bsl[4] = {0.0, 0.0, 0.0, 0.0};
-        if (W != 0.0) {
-          const PairPrim bra = load_pair(brec, bl);
+        const PairPrim bra = load_pair(brec, bl);
+        if (W != 0.0 && !(s.zero_skip && pair_underflowed(bra.K))) {
           double bs[4] = {0.0, 0.0, 0.0, 0.0};
           if (LA) bs[0] = brec[ia * 16 + bl];
           if (LB) bs[1] = brec[ib * 16 + bl];
@@ -622,6 +625,7 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
           for (int pk = 0; pk < kn; ++pk) {
             const double* krec = sket + (k0 + pk) * kPairFields * 16;
             const PairPrim ket = load_pair(krec, kt);
+            if (s.zero_skip && pair_underflowed(ket.K)) continue;
             double ds[4] = {0.0, 0.0, 0.0, 0.0};
             if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
             if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
@@ -786,6 +790,7 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
         double bsl[4] = {0.0, 0.0, 0.0, 0.0};
         const PairPrim bra = load_pair(brec, bl);
+        if (s.zero_skip && pair_underflowed(bra.K)) continue;
         double bs[4] = {0.0, 0.0, 0.0, 0.0};
         if (LA) bs[0] = brec[ia * 16 + bl];
         if (LB) bs[1] = brec[ib * 16 + bl];
@@ -794,6 +799,7 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         for (int pk = 0; pk < kn; ++pk) {
           const double* krec = sket + (k0 + pk) * kPairFields * 16;
           const PairPrim ket = load_pair(krec, kt);
+          if (s.zero_skip && pair_underflowed(ket.K)) continue;
           double ds[4] = {0.0, 0.0, 0.0, 0.0};
           if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
           if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];

@@ -46,6 +46,8 @@ struct SystemDev {
   const double* bp_kmax;   // [nbp]  max |K_ab| over the primitive-pair records of each block pair
   double screen;           // opt-in tile screening threshold (0: off)
   unsigned long long* skipped;   // counter of skipped tiles (screening on)
+  int zero_skip;                 // 1 (default): primitive pairs whose Gaussian product underflowed to exactly 0 are left out of the loops
+  unsigned long long* underflowed;   // counter: such primitive pairs (valid lanes), written by k_pairs
   unsigned long long* zero_weight;   // counter of contracted quartets the gradient pass skipped because their weight is exactly 0
 };
 

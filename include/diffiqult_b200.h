@@ -77,6 +77,10 @@ typedef struct dq_stats {
   int64_t n_grad_quartets_zero_weight;  /* contracted quartets of this rank whose two-particle weight in the ERI-gradient pass is
                             * EXACTLY 0.0 (both density-like factors vanish identically, e.g. between uncoupled far-apart
                             * fragments): they add exactly nothing and their primitive loops are skipped */
+  int64_t n_prim_pairs;    /* primitive pairs over all function-block pairs (both orders of a diagonal block counted) */
+  int64_t n_prim_pairs_underflowed;  /* ... of which the Gaussian-product exponential underflowed to EXACTLY 0: primitive
+                            * quartets containing one are exact zeros (value and every derivative) and are left out of the
+                            * kernels' loops - bit-identical results; DQ_NO_ZERO_SKIP=1 evaluates them anyway */
   int32_t grad_kernel_sparse;   /* 1: the ERI-gradient pass used the lane-independent kernel for sparse weights (chosen when
                                  * fewer than 25 % of the elements of the final density matrix are nonzero), 0: the dense one */
 } dq_stats;

@@ -660,3 +660,31 @@ def test_sparse_weight_gradient_kernel_equals_dense(monkeypatch):
     # every monomer is a rigidly rotated copy plus jitter: the centre gradient of the whole cluster sums to ~0 per monomer
     # only up to the jitter, but translational invariance of the TOTAL energy holds exactly for floating Gaussians + nuclei
     # moved together; here only the Gaussians move, so no such identity applies - the dense kernel is the reference.
+
+
+def test_exact_zero_primitive_pairs_are_skipped_bit_identically(monkeypatch):
+    """Primitive pairs whose Gaussian product underflows to exactly 0 are left out of the kernels' loops (marker K = -0.0):
+    same energy and gradient to the last bits as with DQ_NO_ZERO_SKIP=1, on monomers far enough apart for underflow; and a
+    primitive with coefficient exactly 0 (value contributions vanish, d/d(coef) does not) still gets its gradient."""
+    mol = synthetic.water_cluster(8, spacing=40.0)
+    s = System_mol(mol, basis_set_3G_STO, 80, "w8far")
+    args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+    a = Energy.rhf_grad(*args, max_scf=100)
+    assert a["stats"]["n_prim_pairs_underflowed"] > 0.3 * a["stats"]["n_prim_pairs"]
+    monkeypatch.setenv("DQ_NO_ZERO_SKIP", "1")
+    b = Energy.rhf_grad(*args, max_scf=100)
+    monkeypatch.delenv("DQ_NO_ZERO_SKIP")
+    assert a["niter"] == b["niter"] and abs(a["E"] - b["E"]) < 1e-11
+    for n in range(3):
+        assert np.abs(a["grad"][n] - b["grad"][n]).max() < 1e-12
+    # zero coefficient: CH2O with the middle primitive of the first function switched off
+    s = sysmol("ch2o")
+    coef = np.array(s.coef, dtype=float)
+    coef[1] = 0.0
+    r = Energy.rhf_grad(np.log(s.alpha), coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100)
+    s.coef = coef
+    ao = orc.SysArrays(s)
+    o = orc.rhf(ao, max_scf=100)
+    assert r["niter"] == o["niter"] and abs(r["E"] - o["E"]) < TOL_E
+    og = orc.rhf_grad(ao, 1, max_scf=100)
+    assert abs(og["grad"][1]) > 1e-3 and np.abs(r["grad"][1] - og["grad"]).max() < TOL_G
