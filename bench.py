@@ -45,6 +45,16 @@ def executed_counts():
         return None
 
 
+def expanded_counts():
+    """The same counts measured before any exact-zero skipping existed (every primitive quartet expanded): the kernels'
+    dense-work efficiency, for comparison with the lane-divergent zero-skipping run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_executed_expanded.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -243,8 +253,22 @@ def run_ours(args):
                     "traffic": ex[key].get("dram_bytes_per_step") if ex else None, "achieved_basis": basis, "peak_source": peak_src,
                     "fp64_pipe_active_ncu": ex[key].get("pipe_fp64_active_frac") if ex else None,
                     "algorithmic": {"flop_per_primitive_quartet": alg_flop, "achieved": alg, "frac": alg / peak.value, "note": alg_note}}
+        exd = expanded_counts()
+
+        def dense_ref(key):
+            if not exd or key not in exd:
+                return None
+            e = exd[key]
+            return {"executed_tflops": e["executed_tflops_under_ncu"], "frac": e["executed_tflops_under_ncu"] / peak.value,
+                    "fp64_pipe_active_ncu": e["pipe_fp64_active_frac"], "ms": e["ms_under_ncu"],
+                    "what": "the same kernel family with EVERY primitive quartet expanded (before exact-zero skipping; "
+                            "profiles/fp64_executed_expanded.json): its dense-work efficiency.  With zero skipping the step is "
+                            "faster but lanes whose primitive pair vanished idle next to lanes whose pair did not, so the "
+                            "executed-flop rate and `frac` above are lower than this"}
         k_val = tile_kernel("k_eri_tiles", ms_eri_kernel, ach_eri, alg_eri, FLOP_VALUE, "k_eri_tiles")
+        k_val["all_quartets_expanded"] = dense_ref("k_eri_tiles")
         k_grad = tile_kernel(gk, ms_grad_kernel, achieved, alg_grad, FLOP_GRAD, gk)
+        k_grad["all_quartets_expanded"] = dense_ref("k_eri_grad_tiles")
         # the dominant kernel family of the step leads; the other tile kernel and the HBM-bound J/K kernel follow
         roofline = dict(k_val if ms_eri_kernel >= ms_grad_kernel else k_grad)
         roofline["other_tile_kernel"] = k_grad if ms_eri_kernel >= ms_grad_kernel else k_val
