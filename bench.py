@@ -268,7 +268,7 @@ def run_ours(args):
         k_val = tile_kernel("k_eri_tiles", ms_eri_kernel, ach_eri, alg_eri, FLOP_VALUE, "k_eri_tiles")
         k_val["all_quartets_expanded"] = dense_ref("k_eri_tiles")
         k_grad = tile_kernel(gk, ms_grad_kernel, achieved, alg_grad, FLOP_GRAD, gk)
-        k_grad["all_quartets_expanded"] = dense_ref("k_eri_grad_tiles")
+        k_grad["all_quartets_expanded"] = dense_ref("k_eri_grad_chunks")
         # the dominant kernel family of the step leads; the other tile kernel and the HBM-bound J/K kernel follow
         roofline = dict(k_val if ms_eri_kernel >= ms_grad_kernel else k_grad)
         roofline["other_tile_kernel"] = k_grad if ms_eri_kernel >= ms_grad_kernel else k_val
