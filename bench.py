@@ -224,11 +224,12 @@ def run_ours(args):
         # the ncu counts are data dependent: they hold for the default workload only
         ex = executed_counts() if (args.spacing == 24.0 and args.waters == 32 and args.screen <= 0) else None
         gk = "k_eri_grad_sparse" if st["grad_kernel_sparse"] else "k_eri_grad_chunks"
-        if ex and gk not in ex:
+        vk = "k_eri_tiles_compact" if st["eri_kernel_compact"] else "k_eri_tiles"
+        if ex and (gk not in ex or vk not in ex):
             ex = None
         if ex:
             achieved = npq * ex[gk]["flop_per_primitive_quartet"] / (ms_grad_kernel * 1e-3) * 1e-12
-            ach_eri = npq * ex["k_eri_tiles"]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
+            ach_eri = npq * ex[vk]["flop_per_primitive_quartet"] / (ms_eri_kernel * 1e-3) * 1e-12
             basis = ("EXECUTED FP64 flop per primitive quartet on this workload (ncu smsp__sass_thread_inst_executed_op_"
                      "{2*dfma,dmul,dadd}_pred_on summed over the 7 class launches, %s) x primitive quartets / live CUDA-event "
                      "time of those launches" % ex.get("source", "profiles/fp64_executed.json"))
@@ -265,7 +266,7 @@ def run_ours(args):
                             "profiles/fp64_executed_expanded.json): its dense-work efficiency.  With zero skipping the step is "
                             "faster but lanes whose primitive pair vanished idle next to lanes whose pair did not, so the "
                             "executed-flop rate and `frac` above are lower than this"}
-        k_val = tile_kernel("k_eri_tiles", ms_eri_kernel, ach_eri, alg_eri, FLOP_VALUE, "k_eri_tiles")
+        k_val = tile_kernel(vk, ms_eri_kernel, ach_eri, alg_eri, FLOP_VALUE, vk)
         k_val["all_quartets_expanded"] = dense_ref("k_eri_tiles")
         k_grad = tile_kernel(gk, ms_grad_kernel, achieved, alg_grad, FLOP_GRAD, gk)
         k_grad["all_quartets_expanded"] = dense_ref("k_eri_grad_chunks")

@@ -35,7 +35,7 @@ class dq_stats(C.Structure):
                 ("n_quartets", C.c_int64), ("n_prim_quartets", C.c_int64), ("scf_iterations", C.c_int32),
                 ("fock_builds", C.c_int32), ("grad_terms", C.c_int32), ("jk_direct", C.c_int32), ("n_tiles_skipped", C.c_int64),
                 ("ms_jk", C.c_double), ("n_grad_quartets_zero_weight", C.c_int64), ("n_prim_pairs", C.c_int64),
-                ("n_prim_pairs_underflowed", C.c_int64), ("grad_kernel_sparse", C.c_int32)]
+                ("n_prim_pairs_underflowed", C.c_int64), ("grad_kernel_sparse", C.c_int32), ("eri_kernel_compact", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -190,6 +190,7 @@ struct Prepared {
   double* d_store = nullptr;
   unsigned long long* d_skipped = nullptr;
   unsigned long long* d_underflowed = nullptr;
+  bool eri_compact = false;     // value pass: compact the surviving primitive pairs per tile (many underflowed Gaussian products)
   bool direct = false;          // integral-direct Fock builds: tiles recomputed batch by batch into d_batch
   double* d_batch = nullptr; size_t batch_tiles = 0;
   bool log_alpha = false;
@@ -411,6 +412,18 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   P.sd.underflowed = P.d_underflowed;
   launch_pairs(st, P.sd, P.d_pd, d_kmax);
   P.sd.underflowed = nullptr;
+  {
+    const char* force = getenv("DQ_ERI_KERNEL");
+    if (force) P.eri_compact = force[0] == 'c';
+    else if (P.sd.zero_skip) {
+      unsigned long long uf = 0;
+      CU(cudaMemcpyAsync(&uf, P.d_underflowed, sizeof uf, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      long long tot = 0;
+      for (const BlockPair& b : P.bps) tot += (long long)b.KK * b.nI * b.nJ;
+      P.eri_compact = (double)uf > 0.25 * (double)tot;
+    }
+  }
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
 
@@ -441,9 +454,14 @@ static void compute_eri_store(Prepared& P) {
   // made the pass time erratic (129-148 ms from run to run)
   for (int c = 15; c >= 0; --c) {        // p-rich (long) classes first
     if (P.cls_start[c + 1] == P.cls_start[c]) continue;
-    launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
-                     P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
+    if (P.eri_compact)
+      launch_eri_tiles_compact(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
+                               P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
+    else
+      launch_eri_tiles(P.ws.st, c, P.d_tiles + P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd,
+                       P.d_store + (size_t)P.cls_start[c] * kTile, P.kkmax);
   }
+  t_stats.eri_kernel_compact = P.eri_compact ? 1 : 0;
 }
 
 // unsort an N x N matrix (rows and/or columns) into the caller's ordering

@@ -266,6 +266,127 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
   store[(long long)blockIdx.x * kTile + threadIdx.x] = v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ERI tiles for systems in which many Gaussian products underflow (selected by the host from the count k_pairs makes).
+// With the per-lane skip of k_eri_tiles, lanes whose primitive pair vanished idle beside lanes whose pair survived (a
+// block holds O 1s next to H 1s).  Here the CTA first COMPACTS: the surviving (lane, primitive) entries of the bra and of
+// the ket are listed (ordered ballots: deterministic), and the primitive quartets of the tile are the Cartesian product
+// of the two lists.  A thread owns ONE ket entry (record in registers) and walks a contiguous share of the bra list - the
+// threads of a warp walk the same share, so the bra records are broadcast loads - adding each primitive integral to a
+// private shared-memory cell per bra lane; a last pass sums, for every quartet, the cells of the ket entries of its lane.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int compact_entries(const double* __restrict__ srec, int KK, int nI, int nJ, unsigned short* list,
+                                               int* lane_start, int* s_wc, int tid) {
+  // entries e = lane*KK + pp, lane-major; survivors (valid lane, K != 0) are written in order; lane_start[l] = number of
+  // survivors with lane < l (lane_start[16] = total).  Returns the total (valid after the final barrier).
+  const int ne = 16 * KK;
+  int base = 0;
+  for (int e0 = 0; e0 < ne; e0 += 256) {
+    const int e = e0 + tid;
+    const int lane = e < ne ? e / KK : 0, pp = e - lane * KK;
+    const bool alive = e < ne && (lane >> 2) < nI && (lane & 3) < nJ && srec[pp * kPairFields * 16 + 80 + lane] != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if ((tid & 31) == 0) s_wc[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int pre = base;
+    for (int w = 0; w < (tid >> 5); ++w) pre += s_wc[w];
+    const int pos = pre + __popc(bal & ((1u << (tid & 31)) - 1u));
+    if (alive) list[pos] = (unsigned short)e;
+    if (e < ne && pp == 0) lane_start[lane] = pos;
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_wc[w];
+    base += tot;
+    __syncthreads();
+  }
+  if (tid == 0) lane_start[16] = base;
+  return base;
+}
+
+template <bool LA, bool LB, bool LC, bool LD>
+__global__ void __launch_bounds__(256, 3) k_eri_tiles_compact(const Tile* __restrict__ tiles, SystemDev s,
+                                                           const double* __restrict__ pd, double* __restrict__ store) {
+  extern __shared__ double sm[];
+  __shared__ int s_wc[8];
+  __shared__ int s_bstart[17], s_kstart[17];
+  if (tile_screened(s, tiles[blockIdx.x])) {
+    store[(long long)blockIdx.x * kTile + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) atomicAdd(s.skipped, 1ULL);
+    return;
+  }
+  const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
+  const int tid = threadIdx.x;
+  const int KKb = c.b1.KK, KKk = c.b2.KK;
+  double* sbra = sm;
+  double* sket = sbra + KKb * kPairFields * 16;
+  double* acc = sket + KKk * kPairFields * 16;                  // [16 bra lanes][256 threads]
+  unsigned short* lb = (unsigned short*)(acc + 16 * 256);       // [16 * KKb]
+  unsigned short* lk = lb + 16 * KKb;                           // [16 * KKk]
+  stage_pairs(c, pd, sbra, sket);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r * 256 + tid] = 0.0;
+  __syncthreads();
+  const int NB = compact_entries(sbra, KKb, c.b1.nI, c.b1.nJ, lb, s_bstart, s_wc, tid);
+  const int NK = compact_entries(sket, KKk, c.b2.nI, c.b2.nJ, lk, s_kstart, s_wc, tid);
+  __syncthreads();
+  double val = 0.0;                     // quartet (bra lane c.bl, ket lane c.kt) of this thread
+  if (NB > 0 && NK > 0) {
+    const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+    const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+    for (int kc0 = 0; kc0 < NK; kc0 += 256) {
+      const int nkc = NK - kc0 < 256 ? NK - kc0 : 256;
+      const int parts = 256 / nkc;
+      const int part = tid / nkc, ikl = tid - part * nkc;
+      if (part < parts) {
+        const int ek = lk[kc0 + ikl];
+        const int ktl = ek / KKk, pk = ek - ktl * KKk;
+        const double* krec = sket + pk * kPairFields * 16;
+        const PairPrim ket = load_pair(krec, ktl);
+        double ks[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LA) ks[0] = krec[ia * 16 + ktl];
+        if (LB) ks[1] = krec[ib * 16 + ktl];
+        if (LC) ks[2] = krec[ic * 16 + ktl];
+        if (LD) ks[3] = krec[id * 16 + ktl];
+        const int share = (NB + parts - 1) / parts;
+        const int b0 = part * share, b1e = b0 + share < NB ? b0 + share : NB;
+        int curbl = -1;
+        double cur = 0.0;
+        for (int ibx = b0; ibx < b1e; ++ibx) {
+          const int eb = lb[ibx];
+          const int bll = eb / KKb, pb = eb - bll * KKb;
+          const double* brec = sbra + pb * kPairFields * 16;
+          const PairPrim bra = load_pair(brec, bll);
+          double ds[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) ds[0] = brec[ia * 16 + bll] - ks[0];
+          if (LB) ds[1] = brec[ib * 16 + bll] - ks[1];
+          if (LC) ds[2] = brec[ic * 16 + bll] - ks[2];
+          if (LD) ds[3] = brec[id * 16 + bll] - ks[3];
+          const double v = prim_quartet<LA, LB, LC, LD, false>(bra, ket, ds, dl, c_boys, 0.0, nullptr);
+          if (bll != curbl) {
+            if (curbl >= 0) acc[curbl * 256 + tid] += cur;
+            curbl = bll; cur = 0.0;
+          }
+          cur += v;
+        }
+        if (curbl >= 0) acc[curbl * 256 + tid] += cur;
+      }
+      __syncthreads();
+      {     // this ket chunk's contribution to the quartet of this thread
+        const int lo = (s_kstart[c.kt] > kc0 ? s_kstart[c.kt] : kc0) - kc0;
+        const int hi = (s_kstart[c.kt + 1] < kc0 + nkc ? s_kstart[c.kt + 1] : kc0 + nkc) - kc0;
+        for (int p = 0; p < parts; ++p)
+          for (int x = lo; x < hi; ++x) val += acc[c.bl * 256 + p * nkc + x];
+      }
+      __syncthreads();
+      if (kc0 + 256 < NK) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r * 256 + tid] = 0.0;
+        __syncthreads();
+      }
+    }
+  }
+  store[(long long)blockIdx.x * kTile + tid] = val;
+}
+
 // tile store -> reference order: Eri_vec[eri_index(i,j,k,l)] with ORIGINAL function indices (Tools.py:25-51)
 __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__ tiles, SystemDev s, const int* __restrict__ f_orig,
                                                         const double* __restrict__ store, double* __restrict__ packed) {
@@ -1641,6 +1762,20 @@ static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, 
     case 14: CALL(true, true, true, false); break;   case 15: CALL(true, true, true, true); break;     \
   }
 
+template <bool A, bool B, bool C, bool D>
+static void eri_compact_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
+  ensure_dynamic_smem(k_eri_tiles_compact<A, B, C, D>, smem > 64 * 1024 ? smem : 64 * 1024, true);
+  k_eri_tiles_compact<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
+}
+void launch_eri_tiles_compact(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
+                              int kkmax) {
+  if (nt <= 0) return;
+  const size_t smem = (size_t)2 * kkmax * kPairFields * 16 * sizeof(double) + (size_t)16 * 256 * sizeof(double) +
+                      (size_t)2 * 16 * kkmax * sizeof(unsigned short) + 16;
+#define CALL(a, b, c, d) eri_compact_launch<a, b, c, d>(st, tiles, nt, s, pd, store, smem)
+  DQ_CLASS_SWITCH(cls, CALL)
+#undef CALL
+}
 void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
                       int kkmax) {
   if (nt <= 0) return;

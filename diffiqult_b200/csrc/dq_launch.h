@@ -39,6 +39,9 @@ void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double*
 void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar, double* g_alpha,
                               double* g_coef, double* g_xyz);
 void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, int kkmax);
+// the same tiles with the surviving primitive pairs compacted first (systems with many underflowed Gaussian products)
+void launch_eri_tiles_compact(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
+                              int kkmax);
 void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
                             const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
 // sparse-weight variant (chunks of <= 32 tiles) and the nonzero count the host chooses by

@@ -83,6 +83,8 @@ typedef struct dq_stats {
                             * kernels' loops - bit-identical results; DQ_NO_ZERO_SKIP=1 evaluates them anyway */
   int32_t grad_kernel_sparse;   /* 1: the ERI-gradient pass used the lane-independent kernel for sparse weights (chosen when
                                  * fewer than 25 % of the elements of the final density matrix are nonzero), 0: the dense one */
+  int32_t eri_kernel_compact;   /* 1: the ERI pass used the kernel that compacts the surviving primitive pairs per tile (chosen
+                                 * when more than 25 % of the primitive-pair prefactors underflowed to exactly 0), 0: the plain one */
 } dq_stats;
 
 /* Work decomposition of the ERI passes for one rank, computed on the host only (usable without a GPU):

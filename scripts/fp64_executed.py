@@ -1,7 +1,7 @@
 """profiles/fp64_executed.json from an ncu metrics pass over the ERI tile kernels and the J/K kernel of one bench step.
 
 On the GPU box (after the same command has exited 0 without ncu):
-    ncu --clock-control none --csv --log-file gpurun_out/fp64.csv -k regex:'k_eri_(grad_)?(tiles|chunks|sparse)|k_jk_cols' -c 39 --metrics \
+    ncu --clock-control none --csv --log-file gpurun_out/fp64.csv -k regex:'k_eri_(grad_)?(tiles|tiles_compact|chunks|sparse)|k_jk_cols' -c 39 --metrics \
       smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,\
       smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,\
       smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,\
@@ -40,7 +40,7 @@ for f, a in fam.items():
     e = {"launches": a["launches"], "ms_under_ncu": a["ns"] * 1e-6, "executed_flop": a["flop"],
          "executed_fp64_thread_instructions": a["inst"], "pipe_fp64_active_frac": a["pipe_ns"] / a["ns"],
          "executed_tflops_under_ncu": a["flop"] / a["ns"] * 1e-3}
-    if f in ("k_eri_tiles", "k_eri_grad_chunks", "k_eri_grad_sparse"):
+    if f in ("k_eri_tiles", "k_eri_tiles_compact", "k_eri_grad_chunks", "k_eri_grad_sparse"):
         e["flop_per_primitive_quartet"] = a["flop"] / npq
         e["fp64_instructions_per_primitive_quartet"] = a["inst"] / npq
         e["dram_bytes_per_step"] = a["dram"]

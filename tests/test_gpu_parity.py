@@ -688,3 +688,25 @@ def test_exact_zero_primitive_pairs_are_skipped_bit_identically(monkeypatch):
     assert r["niter"] == o["niter"] and abs(r["E"] - o["E"]) < TOL_E
     og = orc.rhf_grad(ao, 1, max_scf=100)
     assert abs(og["grad"][1]) > 1e-3 and np.abs(r["grad"][1] - og["grad"]).max() < TOL_G
+
+
+@pytest.mark.parametrize("name", ["h2", "h2o_sto3g", "ch2o", "ch4", "h2_6g", "h2o_mixed"])
+def test_compacting_eri_kernel_equals_plain_and_oracle(monkeypatch, name):
+    """The ERI kernel that lists the surviving primitive pairs of a tile and walks their Cartesian product (chosen
+    automatically when many Gaussian products underflow) forced on ordinary molecules, incl. long (36 primitive pairs:
+    several list chunks) and mixed contractions: packed ERI vector against the plain kernel and the oracle."""
+    table = systems.SYSTEMS if name in systems.SYSTEMS else systems.EXTRA_SYSTEMS
+    mol, basis, ne = table[name]
+    s = System_mol(mol, basis, ne, name)
+    a = orc.SysArrays(s)
+    cn = Integrals.normalization(s.alpha, s.coef, s.l, s.list_contr)
+    monkeypatch.setenv("DQ_ERI_KERNEL", "tiles")
+    e0 = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    monkeypatch.setenv("DQ_ERI_KERNEL", "compact")
+    e1 = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    assert np.abs(e1 - e0).max() < 1e-13 * max(1.0, np.abs(e0).max())
+    assert np.abs(e1 - orc.eri(a, cn)).max() < TOL_INT
+    r = Energy.rhf_grad(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=60)
+    assert r["stats"]["eri_kernel_compact"] == 1
+    o = orc.rhf(a, max_scf=60)
+    assert r["niter"] == o["niter"] and abs(r["E"] - o["E"]) < TOL_E
