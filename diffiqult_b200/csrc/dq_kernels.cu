@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int compact_entries(const double* __restrict__ srec, int KK, int nI, int nJ, unsigned short* list,
                                                int* lane_start, int* s_wc, int tid) {
-  // entries e = lane*KK + pp, lane-major; survivors (valid lane, K != 0) are written in order; lane_start[l] = number of
+  // entries e = lane*KK + pp, lane-major; survivors (valid lane, K != 0) are written in order as (lane << 8 | pp);
+  // lane_start[l] = number of
   // survivors with lane < l (lane_start[16] = total).  Returns the total (valid after the final barrier).
   const int ne = 16 * KK;
   int base = 0;
@@ -291,7 +292,7 @@ __device__ __forceinline__ int compact_entries(const double* __restrict__ srec, 
     int pre = base;
     for (int w = 0; w < (tid >> 5); ++w) pre += s_wc[w];
     const int pos = pre + __popc(bal & ((1u << (tid & 31)) - 1u));
-    if (alive) list[pos] = (unsigned short)e;
+    if (alive) list[pos] = (unsigned short)((lane << 8) | pp);      // (pp < 256: the staging limit keeps KK <= 97)
     if (e < ne && pp == 0) lane_start[lane] = pos;
     int tot = 0;
     for (int w = 0; w < 8; ++w) tot += s_wc[w];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256, 3) k_eri_tiles_compact(const Tile* __rest
       const int part = tid / nkc, ikl = tid - part * nkc;
       if (part < parts) {
         const int ek = lk[kc0 + ikl];
-        const int ktl = ek / KKk, pk = ek - ktl * KKk;
+        const int ktl = ek >> 8, pk = ek & 255;
         const double* krec = sket + pk * kPairFields * 16;
         const PairPrim ket = load_pair(krec, ktl);
         double ks[4] = {0.0, 0.0, 0.0, 0.0};
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256, 3) k_eri_tiles_compact(const Tile* __rest
         double cur = 0.0;
         for (int ibx = b0; ibx < b1e; ++ibx) {
           const int eb = lb[ibx];
-          const int bll = eb / KKb, pb = eb - bll * KKb;
+          const int bll = eb >> 8, pb = eb & 255;
           const double* brec = sbra + pb * kPairFields * 16;
           const PairPrim bra = load_pair(brec, bll);
           double ds[4] = {0.0, 0.0, 0.0, 0.0};
