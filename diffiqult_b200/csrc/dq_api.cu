@@ -317,7 +317,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.N = N; sd.nprim = s->nprim; sd.natoms = s->natoms; sd.nblocks = nb; sd.nbp = P.nbp;
   sd.f_off = P.d_foff; sd.f_type = P.d_ftype; sd.f_block = P.d_fblock; sd.f_xyz = P.d_xyz;
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
-  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr; sd.underflowed = nullptr;
+  sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr; sd.underflowed = nullptr; sd.wmask = nullptr;
   sd.zero_skip = getenv("DQ_NO_ZERO_SKIP") ? 0 : 1;
   }
 
@@ -775,6 +775,11 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
       }
     }
     t_stats.grad_kernel_sparse = sparse ? 1 : 0;
+    if (sparse) {
+      unsigned char* d_mask = ws.alloc<unsigned char>(nn);
+      launch_weight_mask(st, (int)nn, nterms, Bt, d_mask);
+      P.sd.wmask = d_mask;
+    }
     t_fork.init(ws.dev);
     t_fork.begin(st);
     for (int c = 15, lane = 0; c >= 0; --c) {

@@ -866,6 +866,10 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
     *valid = kl < b2.nI && ll < b2.nJ && il < b1.nI && jl < b1.nJ;
     if (!*valid) return 0.0;
     const int i = b1.sI + il, j = b1.sJ + jl, k = b2.sI + kl, l = b2.sJ + ll;
+    if (s.wmask) {       // every product of the weight carries one of these six B factors: all zero -> W is exactly 0
+      const unsigned char* m = s.wmask;
+      if (!(m[k * n + l] | m[i * n + j] | m[j * n + l] | m[i * n + l] | m[j * n + k] | m[i * n + k])) return 0.0;
+    }
     double W = 0.0;
     for (int q = 0; q < nterms; ++q) {
       const double* A = At + q * nn;
@@ -968,6 +972,15 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
     for (int o = 16; o >= 1; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
     if ((tid & 31) == 0 && nzero) atomicAdd(s.zero_weight, (unsigned long long)nzero);
   }
+}
+
+// wmask[x] = 1 iff B_t[x] != 0 for some term t
+__global__ void k_weight_mask(int n2, int nterms, const double* __restrict__ Bt, unsigned char* __restrict__ mask) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n2) return;
+  bool on = false;
+  for (int t = 0; t < nterms && !on; ++t) on = Bt[(size_t)t * n2 + x] != 0.0;
+  mask[x] = on ? 1 : 0;
 }
 
 // number of nonzero elements of an n x n matrix (host decision: dense or sparse gradient kernel)
@@ -1798,6 +1811,9 @@ void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const i
 #define CALL(a, b, c, d) grad_sparse_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, nterms, At, Bt, padj, pasum, smem)
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
+}
+void launch_weight_mask(cudaStream_t st, int n2, int nterms, const double* Bt, unsigned char* mask) {
+  k_weight_mask<<<cdiv(n2, 256), 256, 0, st>>>(n2, nterms, Bt, mask); DQ_LAUNCHED();
 }
 void launch_count_nonzero(cudaStream_t st, int n2, const double* A, int* out) {
   cudaMemsetAsync(out, 0, sizeof(int), st);

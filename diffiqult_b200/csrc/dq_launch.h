@@ -48,6 +48,7 @@ void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const i
 void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
                             const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
 void launch_count_nonzero(cudaStream_t st, int n2, const double* A, int* out);
+void launch_weight_mask(cudaStream_t st, int n2, int nterms, const double* Bt, unsigned char* mask);
 size_t eri_grad_smem_bytes(int kkmax);
 void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const int* f_orig, const double* store,
                            double* packed);

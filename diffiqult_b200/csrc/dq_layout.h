@@ -48,6 +48,7 @@ struct SystemDev {
   unsigned long long* skipped;   // counter of skipped tiles (screening on)
   int zero_skip;                 // 1 (default): primitive pairs whose Gaussian product underflowed to exactly 0 are left out of the loops
   unsigned long long* underflowed;   // counter: such primitive pairs (valid lanes), written by k_pairs
+  const unsigned char* wmask;    // [N*N] gradient pass: is B_t[i,j] nonzero for some term t (every product in a weight has a B factor)
   unsigned long long* zero_weight;   // counter of contracted quartets the gradient pass skipped because their weight is exactly 0
 };
 
