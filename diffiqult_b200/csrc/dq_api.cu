@@ -423,6 +423,10 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       for (const BlockPair& b : P.bps) tot += (long long)b.KK * b.nI * b.nJ;
       P.eri_compact = (double)uf > 0.25 * (double)tot;
     }
+    // the compacting kernel adds 32 KB of partial-sum cells and two entry lists to the staged records
+    const size_t compact_smem = (size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) + 16 * 256 * sizeof(double) +
+                                (size_t)2 * 16 * P.kkmax * sizeof(unsigned short) + 16;
+    if (compact_smem > 220 * 1024) P.eri_compact = false;
   }
   if ((size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) > 200 * 1024) fail(-1, "contraction too long for the ERI kernel's shared-memory staging");
 }
