@@ -54,6 +54,13 @@ void hh_prim_quartet(const double* ex, const double* co, const double* R, const 
   pair_backward(ex[2], co[2], R + 6, l[2], ex[3], co[3], R + 9, l[3], ka, e[2], e[3], grad + 2, grad + 3, grad + 6, grad + 7, grad + 14, grad + 17);
 }
 
+// pair prefactor K of make_pair and the exponential-underflow marker the kernels test
+void hh_pair_prefactor(double a, double ca, const double* A, double b, double cb, const double* B, double* K, int* underflowed) {
+  const PairPrim p = make_pair(a, ca, A, 0, b, cb, B, 0);
+  *K = p.K;
+  *underflowed = pair_underflowed(p.K) ? 1 : 0;
+}
+
 // one primitive pair: S,T,V and their partials wrt (alpha, beta, ca, cb, A[3], B[3]) -> out[3][11]
 void hh_one_electron_primitive(double al, double ca, const double* A, int la, double be, double cb, const double* B, int lb,
                                int natoms, const int* Z, const double* C, double* out) {

@@ -103,3 +103,26 @@ def test_one_electron_primitive_value_and_partials(hh):
             assert not np.isnan(out).any()
             worst = max(worst, (np.abs(out - ref) / np.maximum(np.abs(ref), 1e-2)).max())
     assert worst < 1e-11, worst
+
+
+def test_pair_underflow_marker(hh):
+    """make_pair marks a Gaussian product whose exponential underflowed to exactly 0 with K = -0.0 (the kernels leave such
+    primitive pairs out of their loops); a zero coefficient gives K = +0.0 and is NOT marked (its d/d(coef) path is alive);
+    anything representable, however small, is computed."""
+    A = np.zeros(3)
+    K, u = C.c_double(0), C.c_int(0)
+
+    def call(a, ca, b, cb, R):
+        B = np.array([0.0, 0.0, R])
+        hh.hh_pair_prefactor(C.c_double(a), C.c_double(ca), A.ctypes, C.c_double(b), C.c_double(cb), B.ctypes, C.byref(K), C.byref(u))
+        return K.value, u.value
+    k, m = call(6.44, 1.0, 3.43, 1.0, 24.0)            # mu R^2 = 2.24 * 576 = 1289 > 745: exp underflows
+    assert k == 0.0 and np.signbit(k) and m == 1
+    k, m = call(6.44, -1.0, 3.43, 1.0, 24.0)           # the marker does not depend on the coefficients' signs
+    assert k == 0.0 and np.signbit(k) and m == 1
+    k, m = call(0.38, 1.0, 0.17, 1.0, 24.0)            # mu R^2 = 67.6: tiny but representable
+    assert 0.0 < k < 1e-25 and m == 0
+    k, m = call(0.38, 0.0, 0.17, 1.0, 1.0)             # zero coefficient: value vanishes, not marked
+    assert k == 0.0 and not np.signbit(k) and m == 0
+    k, m = call(0.38, 0.0, 0.17, -1.0, 1.0)
+    assert k == 0.0 and not np.signbit(k) and m == 0
