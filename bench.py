@@ -211,6 +211,30 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
     wall, dev_ms = float(red[0]), float(red[1])
+    # For the record, outside the timed region: the same step with EVERY primitive quartet expanded - no skipping of
+    # underflowed Gaussian products, dense-weight gradient kernel (the library reads these switches on every call).  Same
+    # energy and gradient; this is what the default run saves by not multiplying by exact zeros.
+    expanded = None
+    if not args.no_expanded and args.screen <= 0:
+        os.environ["DQ_NO_ZERO_SKIP"] = "1"
+        os.environ["DQ_GRAD_KERNEL"] = "dense"
+        try:
+            step()
+            barrier()
+            t1 = time.perf_counter()
+            rx = step()
+            barrier()
+            ex_wall = time.perf_counter() - t1
+        finally:
+            del os.environ["DQ_NO_ZERO_SKIP"], os.environ["DQ_GRAD_KERNEL"]
+        redx = torch.tensor([ex_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(redx, op=dist.ReduceOp.MAX)
+        expanded = {"ms_per_step": float(redx[0]) * 1e3, "energy_hartree": rx["E"],
+                    "max_abs_gradient_difference_to_default_run": float(max(np.abs(rx["grad"][n] - r["grad"][n]).max() for n in range(3))),
+                    "phases_ms": {k: rx["stats"][k] for k in ("ms_eri", "ms_scf", "ms_reverse", "ms_eri_grad")},
+                    "what": "one step with DQ_NO_ZERO_SKIP=1 DQ_GRAD_KERNEL=dense (every primitive quartet of both passes expanded "
+                            "wherever its weight is not exactly zero), measured after the timed region"}
     if rank == 0:
         st = stats[-1]
         K = args.steps
@@ -303,6 +327,7 @@ def run_ours(args):
                        "parallelism": "tiles round-robin over %d ranks; allreduce of J|K per Fock build and of the gradient" % world},
             "e2e": {"value": nq / (wall / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(np.sum([x["launches"] for x in stats])),
+            "all_quartets_expanded": expanded,
             "clocks": sampler.summary(),
             "roofline": roofline,
             "phases_ms": {k: float(np.mean([x[k] for x in stats])) for k in
@@ -327,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--waters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-expanded", action="store_true", help="skip the extra all-quartets-expanded step after the timed region")
     ap.add_argument("--ref-waters", type=int, default=REF_SAMPLE_WATERS, help="--impl reference: monomers in the bounded CPU sample")
     ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])
     ap.add_argument("--spacing", type=float, default=24.0, help="grid spacing of the water cluster in bohr (default 24: the "

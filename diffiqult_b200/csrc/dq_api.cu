@@ -422,6 +422,7 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       long long tot = 0;
       for (const BlockPair& b : P.bps) tot += (long long)b.KK * b.nI * b.nJ;
       P.eri_compact = (double)uf > 0.25 * (double)tot;
+      if (uf == 0) P.sd.zero_skip = 0;      // nothing underflowed (compact molecules): the kernels without the skip tests
     }
     // the compacting kernel adds 32 KB of partial-sum cells and two entry lists to the staged records
     const size_t compact_smem = (size_t)2 * P.kkmax * kPairFields * 16 * sizeof(double) + 16 * 256 * sizeof(double) +

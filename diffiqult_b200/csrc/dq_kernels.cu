@@ -221,7 +221,9 @@ __device__ __forceinline__ bool tile_screened(const SystemDev& s, const Tile tl)
   return s.screen > 0.0 && kTwoPi52 * s.bp_kmax[tl.bp1] * s.bp_kmax[tl.bp2] < s.screen;
 }
 
-template <bool LA, bool LB, bool LC, bool LD>
+// ZS: leave primitive pairs with an exactly zero prefactor out of the loops.  A template parameter, not a run-time test:
+// the variant without it is the kernel as it was before the skip existed (a dead branch in these loops costs ~10 %).
+template <bool LA, bool LB, bool LC, bool LD, bool ZS>
 __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd,
                                                    double* __restrict__ store) {
   extern __shared__ double sm[];
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
     for (int pb = 0; pb < c.b1.KK; ++pb) {
       const double* brec = sbra + pb * kPairFields * 16;
       const PairPrim bra = load_pair(brec, c.bl);
-      if (s.zero_skip && bra.K == 0.0) continue;      // exactly zero prefactor: the 9 quartets below are exact zeros
+      if (ZS && bra.K == 0.0) continue;      // exactly zero prefactor: the quartets below are exact zeros
       // the components of P along the axes of the p functions come straight from the staged records at a CTA-uniform
       // offset: no per-primitive select
       double bs[4] = {0.0, 0.0, 0.0, 0.0};
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
       for (int pk = 0; pk < c.b2.KK; ++pk) {
         const double* krec = sket + pk * kPairFields * 16;
         const PairPrim ket = load_pair(krec, c.kt);
-        if (s.zero_skip && ket.K == 0.0) continue;
+        if (ZS && ket.K == 0.0) continue;
         double ds[4] = {0.0, 0.0, 0.0, 0.0};
         if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
         if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
@@ -672,7 +674,7 @@ constexpr int kSparseChunk = 20;   // tiles per chunk of the sparse-weight gradi
 // ---------------------------------------------------------------------------------------------
 // occupancy: up to three p functions the kernel fits two CTAs per SM (128 registers with small spills, 2 x ~105 KB
 // shared memory); (pp|pp) needs > 200 registers and gains nothing from being squeezed (measured)
-template <bool LA, bool LB, bool LC, bool LD>
+template <bool LA, bool LB, bool LC, bool LD, bool ZS>
 __global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
 k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s, const double* __restrict__ pd,
                   int nterms, const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
@@ -738,7 +740,7 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         // once per bra primitive (the axis is CTA-uniform: no select inside the ket loop)
         double bsl[4] = {0.0, 0.0, 0.0, 0.0};
         const PairPrim bra = load_pair(brec, bl);
-        if (W != 0.0 && !(s.zero_skip && pair_underflowed(bra.K))) {
+        if (W != 0.0 && !(ZS && pair_underflowed(bra.K))) {
           double bs[4] = {0.0, 0.0, 0.0, 0.0};
           if (LA) bs[0] = brec[ia * 16 + bl];
           if (LB) bs[1] = brec[ib * 16 + bl];
@@ -747,7 +749,7 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
           for (int pk = 0; pk < kn; ++pk) {
             const double* krec = sket + (k0 + pk) * kPairFields * 16;
             const PairPrim ket = load_pair(krec, kt);
-            if (s.zero_skip && pair_underflowed(ket.K)) continue;
+            if (ZS && pair_underflowed(ket.K)) continue;
             double ds[4] = {0.0, 0.0, 0.0, 0.0};
             if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
             if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
@@ -1754,14 +1756,26 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
-  ensure_dynamic_smem(k_eri_tiles<A, B, C, D>, 200 * 1024, true);
-  k_eri_tiles<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
+  if (s.zero_skip) {
+    ensure_dynamic_smem(k_eri_tiles<A, B, C, D, true>, 200 * 1024, true);
+    k_eri_tiles<A, B, C, D, true><<<nt, 256, smem, st>>>(tiles, s, pd, store);
+  } else {
+    ensure_dynamic_smem(k_eri_tiles<A, B, C, D, false>, 200 * 1024, true);
+    k_eri_tiles<A, B, C, D, false><<<nt, 256, smem, st>>>(tiles, s, pd, store);
+  }
+  DQ_LAUNCHED();
 }
 template <bool A, bool B, bool C, bool D>
 static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
                         int nterms, const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
-  ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D>, 220 * 1024, true);   // 2 CTAs x ~105 KB
-  k_eri_grad_chunks<A, B, C, D><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum); DQ_LAUNCHED();
+  if (s.zero_skip) {
+    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, true>, 220 * 1024, true);   // 2 CTAs x ~105 KB
+    k_eri_grad_chunks<A, B, C, D, true><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum);
+  } else {
+    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, false>, 220 * 1024, true);
+    k_eri_grad_chunks<A, B, C, D, false><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum);
+  }
+  DQ_LAUNCHED();
 }
 
 #define DQ_CLASS_SWITCH(cls, CALL)                                                              \
