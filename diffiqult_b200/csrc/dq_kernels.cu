@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
       }
     }
   }
-  store[(long long)blockIdx.x * kTile + threadIdx.x] = v;
+  // streaming store (evict-first): the 2.6 GB tile stream must not push the 15 MB of pair records, which every CTA
+  // re-reads, out of L2 - the pass is bound by the latency of those reads
+  __stcs(store + (long long)blockIdx.x * kTile + threadIdx.x, v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(256, 3) k_eri_tiles_compact(const Tile* __rest
       }
     }
   }
-  store[(long long)blockIdx.x * kTile + tid] = val;
+  __stcs(store + (long long)blockIdx.x * kTile + tid, val);      // streaming store, see k_eri_tiles
 }
 
 // tile store -> reference order: Eri_vec[eri_index(i,j,k,l)] with ORIGINAL function indices (Tools.py:25-51)
@@ -1792,7 +1794,7 @@ static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, 
 
 template <bool A, bool B, bool C, bool D>
 static void eri_compact_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
-  ensure_dynamic_smem(k_eri_tiles_compact<A, B, C, D>, smem > 64 * 1024 ? smem : 64 * 1024, true);
+  ensure_dynamic_smem(k_eri_tiles_compact<A, B, C, D>, smem > 64 * 1024 ? smem : 64 * 1024, getenv("DQ_CARVEOUT") != nullptr);
   k_eri_tiles_compact<A, B, C, D><<<nt, 256, smem, st>>>(tiles, s, pd, store); DQ_LAUNCHED();
 }
 void launch_eri_tiles_compact(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
