@@ -55,7 +55,11 @@ basis_mixed = {
     1: [('S', basis_set_3G_STO[1][0][1][:2]), ('S', basis_set_3G_STO[1][0][1][2:])],        # 2 + 1 primitives
     8: basis_set_3G_STO[8] + [('P', [(0.9, 1.0)]), ('S', [(0.35, 0.6), (1.7, 0.5), (9.0, 0.2), (40.0, 0.05)])],
 }
+# four hydrogens, one 6-primitive s function each: a full block of 4 functions with 36 primitive pairs per function pair
+# (576 entries per side of a tile: the list-building and ket-chunk loops of the compacting ERI kernel run several rounds)
+H4 = [(1, (0.0, 0.0, 0.0)), (1, (0.0, 0.0, 1.5)), (1, (1.4, 0.3, 0.2)), (1, (-0.4, 1.3, 1.1))]
 EXTRA_SYSTEMS = {
+    "h4_6g": (H4, basis_h_6g, 4),
     "h2_6g": (syn.H2_EXAMPLE, basis_h_6g, 2),
     "h2o_mixed": (syn.H2O, basis_mixed, 10),
 }

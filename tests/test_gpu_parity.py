@@ -690,7 +690,7 @@ def test_exact_zero_primitive_pairs_are_skipped_bit_identically(monkeypatch):
     assert abs(og["grad"][1]) > 1e-3 and np.abs(r["grad"][1] - og["grad"]).max() < TOL_G
 
 
-@pytest.mark.parametrize("name", ["h2", "h2o_sto3g", "ch2o", "ch4", "h2_6g", "h2o_mixed"])
+@pytest.mark.parametrize("name", ["h2", "h2o_sto3g", "ch2o", "ch4", "h2_6g", "h4_6g", "h2o_mixed"])
 def test_compacting_eri_kernel_equals_plain_and_oracle(monkeypatch, name):
     """The ERI kernel that lists the surviving primitive pairs of a tile and walks their Cartesian product (chosen
     automatically when many Gaussian products underflow) forced on ordinary molecules, incl. long (36 primitive pairs:
