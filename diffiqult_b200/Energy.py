@@ -11,6 +11,13 @@ from . import _capi
 SCF_FAILED = 99999  # Energy.py:322
 
 
+def _check_max_scf(max_scf):
+    # Energy.py:164 `for i in range(max_scf)`: with max_scf < 1 the reference runs no iteration and then reads the undefined
+    # E_elec (NameError).  There is no energy to return: reject it here as well.
+    if int(max_scf) < 1:
+        raise ValueError("max_scf must be >= 1 (the reference's SCF loop needs at least one iteration)")
+
+
 def _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log):
     return _capi.SystemArrays(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
 
@@ -28,30 +35,37 @@ def fockmatrix(alpha, coef, xyz, l, charges, atoms, contr_list, D, device=0, jk_
 
 
 def rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
-        world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None):
+        world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None,
+        accumulate="fixed"):
     """Full result of one RHF single point: dict(E, status, niter, esteps, C, eps, stats)."""
+    _check_max_scf(max_scf)
     a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
     n = a.nbasis
     E, nit = C.c_double(0.0), C.c_int32(0)
     es, Cm, eps = np.zeros(max(int(max_scf), 1)), np.zeros((n, n)), np.zeros(n)
     guess = None if guess_C is None else np.ascontiguousarray(guess_C, dtype=np.float64)
     opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce,
-                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess)
+                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess,
+                        accumulate=accumulate)
     st = _capi.check(_capi.lib().dq_rhf(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), es.ctypes, Cm.ctypes,
                                         eps.ctypes), allow=(0, 1))
     return dict(E=E.value, status=st, niter=nit.value, esteps=es[:nit.value].copy(), C=Cm, eps=eps, stats=_capi.stats())
 
 
 def rhf_grad(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
-             world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None):
+             world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None,
+             accumulate="fixed"):
     """Energy and its gradient w.r.t. (alpha as passed, raw coefficients, Gaussian centres) in one fused pass:
-    dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats)."""
+    dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats).  accumulate="fixed" (default): order-independent
+    fixed-point sums, two calls on the same inputs return identical bits; "float": floating-point atomics."""
+    _check_max_scf(max_scf)
     a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
     E, nit = C.c_double(0.0), C.c_int32(0)
     ga, gc, gx = np.zeros(a.nprim), np.zeros(a.nprim), np.zeros(3 * a.nbasis)
     guess = None if guess_C is None else np.ascontiguousarray(guess_C, dtype=np.float64)
     opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce,
-                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess)
+                        jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess,
+                        accumulate=accumulate)
     st = _capi.check(_capi.lib().dq_rhf_grad(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), ga.ctypes, gc.ctypes,
                                              gx.ctypes), allow=(0, 1))
     return dict(E=E.value, status=st, niter=nit.value, grad=[ga, gc, gx], stats=_capi.stats())

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libdiffiqult_b200.so")
 
-ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)   # (dev ptr, count, cudaStream_t, user)
 
 
 class dq_system(C.Structure):
@@ -25,7 +25,7 @@ class dq_options(C.Structure):
     _fields_ = [("max_scf", C.c_int32), ("e_tol", C.c_double), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("world_size", C.c_int32), ("rank", C.c_int32), ("allreduce", ALLREDUCE_FN),
                 ("allreduce_user", C.c_void_p), ("jk_mode", C.c_int32), ("direct_batch_bytes", C.c_int64),
-                ("screen_threshold", C.c_double), ("guess_C", C.c_void_p)]
+                ("screen_threshold", C.c_double), ("guess_C", C.c_void_p), ("accumulate", C.c_int32)]
 
 
 class dq_stats(C.Structure):
@@ -127,11 +127,13 @@ _noop_allreduce = ALLREDUCE_FN()
 
 
 JK_MODES = {"auto": 0, "stored": 1, "direct": 2}
+ACCUMULATE = {"default": 0, "fixed": 1, "float": 2}
 
 
 def options(max_scf=30, e_tol=0.0, device=0, stream=None, world_size=1, rank=0, allreduce=None, jk_mode="auto",
-            direct_batch_bytes=0, screen_threshold=0.0, guess_C=None):
+            direct_batch_bytes=0, screen_threshold=0.0, guess_C=None, accumulate="fixed"):
     return dq_options(int(max_scf), float(e_tol), int(device), C.c_void_p(stream) if stream else None, int(world_size),
                       int(rank), allreduce if allreduce is not None else _noop_allreduce, None,
                       JK_MODES[jk_mode] if isinstance(jk_mode, str) else int(jk_mode), int(direct_batch_bytes),
-                      float(screen_threshold), guess_C.ctypes.data if guess_C is not None else None)
+                      float(screen_threshold), guess_C.ctypes.data if guess_C is not None else None,
+                      ACCUMULATE[accumulate] if isinstance(accumulate, str) else int(accumulate))

@@ -30,7 +30,7 @@ def same_structure(systems):
     return True
 
 
-def rhf_grad_batch_fused(systems, max_scf=30, device=0, with_grad=True, log=True, stream=None):
+def rhf_grad_batch_fused(systems, max_scf=30, device=0, with_grad=True, log=True, stream=None, accumulate="fixed"):
     """All molecules in one set of launches (they must share one structure).  Returns (E[n], status[n], grads, stats) with
     grads[i] = [d/d ln(alpha), d/d coef, d/d xyz] as Energy.rhf_grad returns them."""
     s0, n = systems[0], len(systems)
@@ -41,7 +41,7 @@ def rhf_grad_batch_fused(systems, max_scf=30, device=0, with_grad=True, log=True
     atoms = np.ascontiguousarray([np.ravel(s.atom) for s in systems], dtype=np.float64)
     E, status, niter = np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
     ga, gc, gx = np.zeros((n, a0.nprim)), np.zeros((n, a0.nprim)), np.zeros((n, 3 * a0.nbasis))
-    opt = _capi.options(max_scf=max_scf, device=device, stream=stream)
+    opt = _capi.options(max_scf=max_scf, device=device, stream=stream, accumulate=accumulate)
     _capi.check(_capi.lib().dq_rhf_grad_batch(C.byref(a0.struct), C.c_int32(n), atoms.ctypes, alpha.ctypes, coef.ctypes, xyz.ctypes,
                                               C.byref(opt), C.c_int32(1 if with_grad else 0), E.ctypes, status.ctypes, niter.ctypes,
                                               ga.ctypes, gc.ctypes, gx.ctypes))

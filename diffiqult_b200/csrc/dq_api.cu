@@ -46,6 +46,21 @@ static void check_launches(const char* where) {
   }
 }
 
+// A Boys-function loop that ran out of terms raised the device flag (non-finite argument; the reference exits the process
+// there, Tools.py:124-125, 150-151): report it as status -5 and clear the flag.  Call after the stream has been drained.
+static void check_boys(cudaStream_t st) {
+  int* flag = boys_fail_flag();
+  if (!flag) return;
+  int h = 0;
+  if (cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return;
+  if (h) {
+    cudaMemsetAsync(flag, 0, sizeof h, st);
+    cudaStreamSynchronize(st);
+    t_err = "Boys function: series / continued fraction did not converge (non-finite argument); the reference exits here (Tools.py:124-125, 150-151)";
+    throw Fail{-5};
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device-memory pool: freed blocks are kept (per device, by exact size) and handed out again, so that repeated
 // calls on the same problem -- every BFGS step, every bench step -- do not pay cudaMalloc/cudaFree of the 2.6 GB tile
@@ -84,12 +99,14 @@ struct Pool {
 };
 static Pool g_pool;
 
+static void sync_side_streams();
 struct Workspace {
   cudaStream_t st = 0;
   int dev = 0;
   std::vector<std::pair<void*, size_t>> owned;
   ~Workspace() {
     cudaStreamSynchronize(st);
+    sync_side_streams();      // an error between ForkJoin::begin and ::end leaves class kernels running on the side streams
     for (auto& b : owned) g_pool.put(dev, b.second, b.first);
   }
   template <class T> T* alloc(size_t n, bool zero = false) {
@@ -122,6 +139,7 @@ struct ForkJoin {
   cudaStream_t side[kSide] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[kSide] = {nullptr, nullptr, nullptr, nullptr};
   int dev = -1;
+  bool open = false;        // begin() without end(): work may be in flight on the side streams
   void init(int d) {
     if (dev == d) return;
     for (int i = 0; i < kSide; ++i) {
@@ -131,11 +149,13 @@ struct ForkJoin {
     cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
     dev = d;
   }
-  void begin(cudaStream_t main) { cudaEventRecord(fork, main); for (int i = 0; i < kSide; ++i) cudaStreamWaitEvent(side[i], fork, 0); }
+  void begin(cudaStream_t main) { open = true; cudaEventRecord(fork, main); for (int i = 0; i < kSide; ++i) cudaStreamWaitEvent(side[i], fork, 0); }
   cudaStream_t lane(int i) const { return side[i % kSide]; }
-  void end(cudaStream_t main) { for (int i = 0; i < kSide; ++i) { cudaEventRecord(join[i], side[i]); cudaStreamWaitEvent(main, join[i], 0); } }
+  void end(cudaStream_t main) { for (int i = 0; i < kSide; ++i) { cudaEventRecord(join[i], side[i]); cudaStreamWaitEvent(main, join[i], 0); } open = false; }
+  void drain() { if (open) { for (int i = 0; i < kSide; ++i) cudaStreamSynchronize(side[i]); open = false; } }
 };
 static thread_local ForkJoin t_fork;
+static void sync_side_streams() { t_fork.drain(); }
 
 // Tile lists depend only on the basis STRUCTURE (types, contraction lengths) and on (world, rank), not on the
 // parameter values: each host thread keeps the last plan, so the repeated calls of an optimisation or of the bench
@@ -152,6 +172,9 @@ struct TilePlan {
   std::vector<Tile> gtiles;
   std::vector<int2> gchunks;
   int gchunk_cls_start[17];
+  std::vector<int2> dchunks;    // integral-direct J/K: runs of <= kDirectChunk tiles sharing the bra block pair (a CTA evaluates AND contracts them)
+  int dchunk_cls_start[17];
+  int2* d_dchunks = nullptr;
   std::vector<int2> gchunks32;  // the same order cut into chunks of <= 20 tiles (sparse-weight gradient kernel: its work list is in shared memory)
   int gchunk32_cls_start[17];
   int2* d_gchunks32 = nullptr;
@@ -165,6 +188,7 @@ struct TilePlan {
     if (d_gtiles) cudaFree(d_gtiles);
     if (d_gchunks) cudaFree(d_gchunks);
     if (d_gchunks32) cudaFree(d_gchunks32);
+    if (d_dchunks) cudaFree(d_dchunks);
   }
 };
 static thread_local std::shared_ptr<TilePlan> t_plan;
@@ -191,8 +215,7 @@ struct Prepared {
   unsigned long long* d_skipped = nullptr;
   unsigned long long* d_underflowed = nullptr;
   bool eri_compact = false;     // value pass: compact the surviving primitive pairs per tile (many underflowed Gaussian products)
-  bool direct = false;          // integral-direct Fock builds: tiles recomputed batch by batch into d_batch
-  double* d_batch = nullptr; size_t batch_tiles = 0;
+  bool direct = false;          // integral-direct Fock builds: every J/K contraction re-evaluates the tiles (k_jk_direct), no tile store
   bool log_alpha = false;
   bool plan_only = false;       // host planning only (dq_plan): no CUDA call is made
   int world = 1, rank = 0;
@@ -319,6 +342,10 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   sd.p_alpha = P.d_alpha; sd.p_coef = P.d_cn; sd.Z = dZ; sd.C = dC; sd.bp = dbp;
   sd.bp_kmax = nullptr; sd.screen = 0.0; sd.skipped = nullptr; sd.zero_weight = nullptr; sd.underflowed = nullptr; sd.wmask = nullptr;
   sd.zero_skip = getenv("DQ_NO_ZERO_SKIP") ? 0 : 1;
+  {
+    const char* acc = getenv("DQ_ACCUM");
+    sd.det = acc ? (acc[1] == 'i' ? 1 : 0) : ((opt && opt->accumulate == 2) ? 0 : 1);     // "fixed" / "float"
+  }
   }
 
   if (!need_tiles) return;
@@ -357,6 +384,19 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
       }
     }
     tp->chunk_cls_start[16] = (int)tp->chunks.size();
+    // a value tile lives 50-100 us: 16 tiles per CTA amortise the per-chunk staging of the bra records and the D / K strips
+    // without leaving long tails
+    const int kDirectChunk = getenv("DQ_DIRECT_CHUNK") ? std::max(1, atoi(getenv("DQ_DIRECT_CHUNK"))) : 16;
+    for (int c = 0; c < 16; ++c) {
+      tp->dchunk_cls_start[c] = (int)tp->dchunks.size();
+      for (int t = tp->cls_start[c]; t < tp->cls_start[c + 1];) {
+        int e = t + 1;
+        while (e < tp->cls_start[c + 1] && e - t < kDirectChunk && tp->tiles[e].bp1 == tp->tiles[t].bp1) ++e;
+        tp->dchunks.push_back(make_int2(t, e - t));
+        t = e;
+      }
+    }
+    tp->dchunk_cls_start[16] = (int)tp->dchunks.size();
     const int kGradChunk = getenv("DQ_GRAD_CHUNK") ? std::max(1, atoi(getenv("DQ_GRAD_CHUNK"))) : 12;
     tp->gtiles = tp->tiles;
     for (int c = 0; c < 16; ++c) {
@@ -382,6 +422,8 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
     }
     tp->gchunk32_cls_start[16] = (int)tp->gchunks32.size();
     if (!P.plan_only) {
+      CU(cudaMalloc(&tp->d_dchunks, std::max<size_t>(tp->dchunks.size(), 1) * sizeof(int2)));
+      CU(cudaMemcpyAsync(tp->d_dchunks, tp->dchunks.data(), tp->dchunks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
       CU(cudaMalloc(&tp->d_gchunks32, std::max<size_t>(tp->gchunks32.size(), 1) * sizeof(int2)));
       CU(cudaMemcpyAsync(tp->d_gchunks32, tp->gchunks32.data(), tp->gchunks32.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
       CU(cudaMalloc(&tp->d_gtiles, std::max<size_t>(tp->gtiles.size(), 1) * sizeof(Tile)));
@@ -443,12 +485,8 @@ static void setup_jk_mode(Prepared& P, const dq_options* opt) {
     CU(cudaMemGetInfo(&fre, &tot));
     P.direct = store_bytes > (fre + g_pool.cached_bytes) / 10 * 7;     // keep 30 % headroom for the SCF history
   }
-  if (P.direct) {
-    size_t bytes = (opt && opt->direct_batch_bytes > 0) ? (size_t)opt->direct_batch_bytes : ((size_t)1 << 30);
-    P.batch_tiles = std::max<size_t>(bytes / (kTile * sizeof(double)), 256);   // at least one full chunk
-    P.batch_tiles = std::min(P.batch_tiles, std::max<size_t>(P.ntiles, 1));
-    P.d_batch = P.ws.alloc<double>(P.batch_tiles * kTile);
-  }
+  if (P.direct && jk_direct_smem_bytes(P.kkmax, P.N, P.sd.det) > 220 * 1024)
+    fail(-1, "basis / contraction too large for the integral-direct kernel's shared-memory staging");
   t_stats.jk_direct = P.direct ? 1 : 0;
 }
 
@@ -480,6 +518,7 @@ static void unsort_matrix(const Prepared& P, const std::vector<double>& in, doub
 // G[D] = 2J - K from the stored tiles (+ allreduce of the partial J|K over ranks); F = H + G if F != null
 struct JK {
   double *JKacc;   // [2*n*n] J accumulators then K accumulators (one buffer: one allreduce)
+  double *JKraw = nullptr;   // fixed-point accumulation: [2*2*n*n] limb pairs the kernel adds into, converted into JKacc
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // brackets of the contraction kernels, read by ms() after a sync
   double ms() {
     double tot = 0.0;
@@ -491,32 +530,33 @@ struct JK {
 static void fock_build(Prepared& P, JK& jk, const double* D, const double* H, double* F, double* G) {
   const int n = P.N;
   cudaStream_t st = P.ws.st;
-  CU(cudaMemsetAsync(jk.JKacc, 0, sizeof(double) * 2 * n * n, st));
+  const bool det = P.sd.det != 0;
+  double* acc = det ? jk.JKraw : jk.JKacc;                       // what the contraction kernel adds into
+  const size_t kofs = (size_t)n * n * (det ? 2 : 1);             // K accumulators follow the J accumulators
+  CU(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * kofs, st));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   jk.ev.push_back({e0, e1});
   CU(cudaEventRecord(e0, st));
   if (!P.direct) {
-    launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, jk.JKacc, jk.JKacc + (size_t)n * n);
+    launch_jk_chunks(st, P.d_tiles, P.d_chunks, P.nchunks, P.sd, P.d_store, D, acc, acc + kofs);
   } else {
-    // integral-direct: for every class, runs of whole chunks that fit the batch buffer are evaluated and contracted at once
+    // integral-direct: one fused evaluate-and-contract kernel per angular class (p-rich, long classes first), the class
+    // launches on side streams so that their tails overlap
     const TilePlan& tp = *P.tp;
-    for (int c = 0; c < 16; ++c) {
-      int c0 = tp.chunk_cls_start[c];
-      const int cend = tp.chunk_cls_start[c + 1];
-      while (c0 < cend) {
-        int c1 = c0; size_t nt = 0;
-        while (c1 < cend && nt + (size_t)tp.chunks[c1].y <= P.batch_tiles) { nt += tp.chunks[c1].y; ++c1; }
-        const int t0 = tp.chunks[c0].x;
-        launch_eri_tiles(st, c, P.d_tiles + t0, (int)nt, P.sd, P.d_pd, P.d_batch, P.kkmax);
-        launch_jk_chunks(st, P.d_tiles, P.d_chunks + c0, c1 - c0, P.sd, P.d_batch - (size_t)t0 * kTile, D, jk.JKacc,
-                         jk.JKacc + (size_t)n * n);
-        c0 = c1;
-      }
+    t_fork.init(P.ws.dev);
+    t_fork.begin(st);
+    for (int c = 15, lane = 0; c >= 0; --c) {
+      const int nch = tp.dchunk_cls_start[c + 1] - tp.dchunk_cls_start[c];
+      if (nch <= 0) continue;
+      launch_jk_direct(t_fork.lane(lane++), c, P.d_tiles, tp.d_dchunks + tp.dchunk_cls_start[c], nch, P.sd, P.d_pd, D, acc, acc + kofs,
+                       P.kkmax);
     }
+    t_fork.end(st);
   }
   CU(cudaEventRecord(e1, st));
-  if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, P.ar_user);
+  if (det) launch_det_finalize(st, (long long)2 * n * n, jk.JKraw, jk.JKacc, 0.0);
+  if (P.world > 1) P.allreduce(jk.JKacc, (int64_t)2 * n * n, (void*)st, P.ar_user);
   launch_fock_combine(st, n, P.d_fblock, H, jk.JKacc, jk.JKacc + (size_t)n * n, F, G);
   t_stats.fock_builds++;
 }
@@ -542,7 +582,8 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   memset(&t_stats, 0, sizeof t_stats);
   reset_launch_count();
   Prepared P;
-  const int max_scf = (opt && opt->max_scf > 0) ? opt->max_scf : 30;
+  if (opt && opt->max_scf < 1) fail(-1, "max_scf must be >= 1 (Energy.py:164: the SCF loop needs at least one iteration)");
+  const int max_scf = opt ? opt->max_scf : 30;
   const double tol = (opt && opt->e_tol > 0) ? opt->e_tol : 1e-8;
   if (s->ne <= 0 || s->ne > s->nbasis) fail(-1, "ne (doubly-occupied orbitals) must be in 1..nbasis");
   cudaStream_t st0 = opt ? (cudaStream_t)opt->stream : 0;
@@ -570,6 +611,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
          *t2 = ws.alloc<double>(nn), *t3 = ws.alloc<double>(nn), *vwork = ws.alloc<double>(nn);
   void* ework = ws.alloc<char>(eigh_workspace_bytes(n, 1));
   JK jk; jk.JKacc = ws.alloc<double>(2 * nn);
+  if (P.sd.det) jk.JKraw = ws.alloc<double>(4 * nn);
   double *F = ws.alloc<double>(nn), *Fp = ws.alloc<double>(nn), *U = ws.alloc<double>(nn), *C = ws.alloc<double>(nn),
          *D = ws.alloc<double>(nn), *eps = ws.alloc<double>(n), *dE = ws.alloc<double>(1);
   // history for the reverse sweep: F_{t-1}, U_t, eps_t, D_t, F_t  (device slabs of 16 iterations: no per-iteration cudaMalloc)
@@ -756,11 +798,16 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     Timer t_g(st);
     if (eri_grad_smem_bytes(P.kkmax) > 220 * 1024) fail(-1, "contraction too long for the ERI-gradient kernel's shared-memory accumulators");
     const long long adj_len = P.pd_len / kPairFields * kAdjFields;
-    double* padj = ws.alloc<double>(adj_len, true);
-    double* pasum = ws.alloc<double>((size_t)P.nbp * 2 * 16, true);
-    // gbuf = [g_alpha | g_coef(normalised) | g_xyz]  (one buffer: one allreduce)
-    double* gbuf = ws.alloc<double>((size_t)2 * P.nprim + 3 * n, true);
+    const bool det = P.sd.det != 0;
+    const int lm = det ? 2 : 1;                  // fixed-point accumulation: every accumulator is a pair of integer limbs
+    double* padj = ws.alloc<double>(adj_len * lm, true);
+    double* pasum = ws.alloc<double>((size_t)P.nbp * 2 * 16 * lm, true);
+    // gbuf = [g_alpha | g_coef(normalised) | g_xyz]  (one buffer: one allreduce); gacc: what the kernels add into
+    const long long glen = (long long)2 * P.nprim + 3 * n;
+    double* gbuf = ws.alloc<double>(glen, true);
+    double* gacc = det ? ws.alloc<double>(2 * glen, true) : gbuf;
     double *ga = gbuf, *gc = gbuf + P.nprim, *gx = gbuf + 2 * P.nprim;
+    double *aa = gacc, *ac = gacc + P.nprim, *ax = gacc + 2 * P.nprim;      // element windows (the kernels index from aa)
     unsigned long long* d_zero = ws.alloc<unsigned long long>(1, true);
     P.sd.zero_weight = d_zero;
     Timer t_gk(st);
@@ -803,9 +850,13 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     t_fork.end(st);
     t_stats.ms_eri_grad = t_gk.stop();
     check_launches("ERI-gradient kernels");
-    launch_pair_bwd(st, P.sd, padj, pasum, ga, gc, gx);
-    if (P.world > 1) P.allreduce(gbuf, (int64_t)2 * P.nprim + 3 * n, P.ar_user);
-    launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, ga, gc, gx);
+    launch_pair_bwd(st, P.sd, padj, pasum, aa, ac, ax);
+    if (det) launch_det_finalize(st, glen, gacc, gbuf, 0.0);
+    if (P.world > 1) P.allreduce(gbuf, (int64_t)glen, (void*)st, P.ar_user);
+    // the one-electron part is replicated (every rank adds the same numbers after the allreduce)
+    if (det) CU(cudaMemsetAsync(gacc, 0, sizeof(double) * 2 * glen, st));
+    launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, aa, ac, ax);
+    if (det) launch_det_finalize(st, glen, gacc, gbuf, 1.0);
     double* graw = ws.alloc<double>(P.nprim);
     launch_normalize_bwd(st, n, P.d_foff, P.d_ftype, P.d_alpha, P.d_craw, gc, ga, graw);
     if (P.log_alpha) launch_mul(st, P.nprim, ga, P.d_alpha, ga);                   // d/d ln(alpha) = alpha d/d alpha
@@ -839,6 +890,7 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
   }
   CU(cudaStreamSynchronize(st));
   check_launches("gradient assembly");
+  check_boys(st);
   t_stats.ms_jk = jk.ms();
   t_stats.ms_total = t_total.stop();
   t_stats.launches = launch_count();
@@ -859,11 +911,14 @@ static void run_batch(const dq_system* shape, int nmol, const double* atoms, con
   if (n > 40) fail(-4, "the batched small-molecule path holds the SCF in shared memory: nbasis <= 40 (use the per-molecule entry points)");
   const int dev = opt ? opt->device : 0;
   need_device(dev);
-  const int max_scf = (opt && opt->max_scf > 0) ? opt->max_scf : 30;
+  if (opt && opt->max_scf < 1) fail(-1, "max_scf must be >= 1 (Energy.py:164: the SCF loop needs at least one iteration)");
+  const int max_scf = opt ? opt->max_scf : 30;
   const double tol = (opt && opt->e_tol > 0) ? opt->e_tol : 1e-8;
   cudaStream_t st = opt ? (cudaStream_t)opt->stream : 0;
   static thread_local int boys_dev = -1;
-  if (boys_dev != dev) { if (upload_boys_constants_batch() != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
+  if (boys_dev != dev) { if (upload_boys_constants_batch(boys_fail_flag()) != 0) fail(-2, "constant upload failed"); boys_dev = dev; }
+  int det = (opt && opt->accumulate == 2) ? 0 : 1;
+  if (const char* acc = getenv("DQ_ACCUM")) det = acc[1] == 'i' ? 1 : 0;
   Timer t_total(st);
 
   // structure tables
@@ -922,6 +977,7 @@ static void run_batch(const dq_system* shape, int nmol, const double* atoms, con
       return d;
     };
     BatchDev b;
+    b.det = det;
     b.nmol = nm; b.N = n; b.nprim = nprim; b.natoms = natoms; b.M = M; b.nrec = nrec; b.neri = neri; b.kkmax = kkmax; b.ne = ne;
     b.f_off = d_foff; b.f_type = d_ftype; b.Z = d_Z; b.pairs = d_pairs; b.pair_off = d_poff; b.rec_pair = d_recp;
     b.atoms = up(atoms + (size_t)m0 * natoms * 3, (size_t)nm * std::max(natoms, 1) * 3);
@@ -955,13 +1011,22 @@ static void run_batch(const dq_system* shape, int nmol, const double* atoms, con
     CU(cudaMemcpyAsync(hc.data(), d_conv, nm * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (want_grad) {
       Timer t_g(st);
-      double* padj = w2.alloc<double>((size_t)nrec * kAdjFields * nm, true);
-      double* pasum = w2.alloc<double>((size_t)M * 2 * nm, true);
-      double *ga = w2.alloc<double>((size_t)nm * nprim, true), *gc = w2.alloc<double>((size_t)nm * nprim, true),
-             *gx = w2.alloc<double>((size_t)nm * n * 3, true), *graw = w2.alloc<double>((size_t)nm * nprim);
+      const int lm = det ? 2 : 1;            // fixed-point accumulators are pairs of integer limbs
+      double* padj = w2.alloc<double>((size_t)nrec * kAdjFields * nm * lm, true);
+      double* pasum = w2.alloc<double>((size_t)M * 2 * nm * lm, true);
+      const size_t na = (size_t)nm * nprim, nx = (size_t)nm * n * 3;
+      double *ga = w2.alloc<double>(na, true), *gc = w2.alloc<double>(na, true), *gx = w2.alloc<double>(nx, true),
+             *graw = w2.alloc<double>(na);
+      double *aa = ga, *ac = gc, *ax = gx;
+      if (det) { aa = w2.alloc<double>(2 * na, true); ac = w2.alloc<double>(2 * na, true); ax = w2.alloc<double>(2 * nx, true); }
       for (int c = 0; c < 16; ++c)
         launch_batch_eri_grad(st, c, b, d_qlist + qstart[c], qstart[c + 1] - qstart[c], terms, d_nterms, max_scf, padj, pasum);
-      launch_batch_grad_finish(st, b, shape->log_alpha != 0, padj, pasum, Sbar, Hbar, ga, gc, gx, graw);
+      launch_batch_grad_accumulate(st, b, padj, pasum, Sbar, Hbar, aa, ac, ax);
+      if (det) {
+        launch_det_finalize(st, (long long)na, aa, ga, 0.0); launch_det_finalize(st, (long long)na, ac, gc, 0.0);
+        launch_det_finalize(st, (long long)nx, ax, gx, 0.0);
+      }
+      launch_batch_grad_finish(st, b, shape->log_alpha != 0, ga, gc, graw);
       if (g_alpha) CU(cudaMemcpyAsync(g_alpha + (size_t)m0 * nprim, ga, (size_t)nm * nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (g_coef) CU(cudaMemcpyAsync(g_coef + (size_t)m0 * nprim, graw, (size_t)nm * nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (g_xyz) CU(cudaMemcpyAsync(g_xyz + (size_t)m0 * n * 3, gx, (size_t)nm * n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -977,6 +1042,7 @@ static void run_batch(const dq_system* shape, int nmol, const double* atoms, con
     }
   }
   check_launches("batched kernels");
+  check_boys(st);
   t_stats.n_quartets = (int64_t)qlist.size() * nmol;
   t_stats.n_prim_quartets = npq * nmol;
   t_stats.ms_total = t_total.stop();
@@ -1044,6 +1110,7 @@ int dq_one_electron(const dq_system* sys, const dq_options* opt, double* S, doub
     CU(cudaStreamSynchronize(P.ws.st));
     if (outs[m]) unsort_matrix(P, h, outs[m], true, true);
   }
+  check_boys(P.ws.st);
   t_stats.launches = launch_count();
   DQ_CATCH
 }
@@ -1059,9 +1126,10 @@ int dq_eri_packed(const dq_system* sys, const dq_options* opt, double* eri) {
   const long long n = P.N, m = n * (n + 1) / 2, len = m * (m + 1) / 2;
   double* dpk = P.ws.alloc<double>(len, true);
   launch_scatter_packed(P.ws.st, P.d_tiles, (int)P.ntiles, P.sd, P.d_forig, P.d_store, dpk);
-  if (P.world > 1) P.allreduce(dpk, len, P.ar_user);
+  if (P.world > 1) P.allreduce(dpk, len, (void*)P.ws.st, P.ar_user);
   CU(cudaMemcpyAsync(eri, dpk, len * sizeof(double), cudaMemcpyDeviceToHost, P.ws.st));
   CU(cudaStreamSynchronize(P.ws.st));
+  check_boys(P.ws.st);
   t_stats.n_tiles = (int64_t)P.ntiles; t_stats.n_quartets = P.n_quartets; t_stats.n_prim_quartets = P.n_prim_quartets;
   t_stats.launches = launch_count();
   DQ_CATCH
@@ -1085,6 +1153,7 @@ int dq_fock(const dq_system* sys, const dq_options* opt, const double* D, double
   double* dD = P.ws.upload(hd);
   double* dF = P.ws.alloc<double>(nn);
   JK jk; jk.JKacc = P.ws.alloc<double>(2 * nn);
+  if (P.sd.det) jk.JKraw = P.ws.alloc<double>(4 * nn);
   fock_build(P, jk, dD, H, dF, nullptr);
   std::vector<double> h(nn);
   CU(cudaMemcpyAsync(h.data(), dF, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1095,6 +1164,7 @@ int dq_fock(const dq_system* sys, const dq_options* opt, const double* D, double
     CU(cudaStreamSynchronize(st));
     unsort_matrix(P, h, Hcore, true, true);
   }
+  check_boys(st);
   t_stats.launches = launch_count();
   DQ_CATCH
 }
@@ -1157,6 +1227,7 @@ int dq_boys(int32_t n, const double* t, double* F, double* dF, int32_t device) {
   launch_boys(0, n, dt, dF_, ddF);
   CU(cudaMemcpy(F, dF_, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(dF, ddF, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  check_boys(0);
   DQ_CATCH
 }
 

@@ -20,9 +20,10 @@ namespace dq {
 
 __constant__ BoysConst c_boys_b;
 
-int upload_boys_constants_batch() {
+int upload_boys_constants_batch(int* fail_flag) {
   BoysConst h;
   boys_const_init(&h);
+  h.fail = fail_flag;
   return (int)cudaMemcpyToSymbol(c_boys_b, &h, sizeof(h));
 }
 
@@ -437,8 +438,8 @@ __global__ void __launch_bounds__(128) kb_eri_grad(BatchDev b, const int2* __res
   const int kkb = b.pair_off[q.x + 1] - b.pair_off[q.x], kkk = b.pair_off[q.y + 1] - b.pair_off[q.y];
   const double* brec0 = b.prec + (size_t)b.pair_off[q.x] * kPairFields * st + mol;
   const double* krec0 = b.prec + (size_t)b.pair_off[q.y] * kPairFields * st + mol;
-  double* badj0 = padj + (size_t)b.pair_off[q.x] * kAdjFields * st + mol;
-  double* kadj0 = padj + (size_t)b.pair_off[q.y] * kAdjFields * st + mol;
+  const long long badj0 = (long long)b.pair_off[q.x] * kAdjFields * st + mol;      // element offsets into padj
+  const long long kadj0 = (long long)b.pair_off[q.y] * kAdjFields * st + mol;
   for (int x = 0; x < kkk * kAdjFields; ++x) sacc[x * 128 + tid] = 0.0;
   double pas = 0.0, pbs = 0.0, qcs = 0.0, qds = 0.0;
   if (W != 0.0) {
@@ -477,15 +478,15 @@ __global__ void __launch_bounds__(128) kb_eri_grad(BatchDev b, const int2* __res
       if (LB) add3(ba.P, ib, bsl[1]);
       if (LC) add3(ba.P, ic, bsl[2]);
       if (LD) add3(ba.P, id_, bsl[3]);
-      double* o = badj0 + (size_t)pb * kAdjFields * st;     // molecule-fastest: the 32 lanes of a warp hit one line
-      atomicAdd(o, ba.P[0]); atomicAdd(o + st, ba.P[1]); atomicAdd(o + 2 * st, ba.P[2]); atomicAdd(o + 3 * st, ba.g);
-      atomicAdd(o + 4 * st, ba.K);
+      const long long o = badj0 + (long long)pb * kAdjFields * st;     // molecule-fastest: the 32 lanes of a warp hit one line
+      acc_add(padj, o, ba.P[0], b.det); acc_add(padj, o + st, ba.P[1], b.det); acc_add(padj, o + 2 * st, ba.P[2], b.det);
+      acc_add(padj, o + 3 * st, ba.g, b.det); acc_add(padj, o + 4 * st, ba.K, b.det);
     }
-    for (int x = 0; x < kkk * kAdjFields; ++x) atomicAdd(kadj0 + (size_t)x * st, sacc[x * 128 + tid]);
-    if (LA) atomicAdd(pasum + ((size_t)q.x * 2 + 0) * st + mol, pas);
-    if (LB) atomicAdd(pasum + ((size_t)q.x * 2 + 1) * st + mol, pbs);
-    if (LC) atomicAdd(pasum + ((size_t)q.y * 2 + 0) * st + mol, qcs);
-    if (LD) atomicAdd(pasum + ((size_t)q.y * 2 + 1) * st + mol, qds);
+    for (int x = 0; x < kkk * kAdjFields; ++x) acc_add(padj, kadj0 + (long long)x * st, sacc[x * 128 + tid], b.det);
+    if (LA) acc_add(pasum, ((long long)q.x * 2 + 0) * st + mol, pas, b.det);
+    if (LB) acc_add(pasum, ((long long)q.x * 2 + 1) * st + mol, pbs, b.det);
+    if (LC) acc_add(pasum, ((long long)q.y * 2 + 0) * st + mol, qcs, b.det);
+    if (LD) acc_add(pasum, ((long long)q.y * 2 + 1) * st + mol, qds, b.det);
   }
 }
 
@@ -505,19 +506,22 @@ __global__ void kb_pair_bwd(BatchDev b, const double* __restrict__ padj, const d
   double Ab[3] = {0, 0, 0}, Bb[3] = {0, 0, 0};
   for (int pp = 0; pp < kk; ++pp) {
     const int p = b.f_off[i] + pp / kj, q = b.f_off[j] + pp % kj;
-    const double* a = padj + (size_t)(b.pair_off[x] + pp) * kAdjFields * st + mol;
-    PairAdj adj; adj.P[0] = a[0]; adj.P[1] = a[st]; adj.P[2] = a[2 * st]; adj.g = a[3 * st]; adj.K = a[4 * st];
+    const long long a = (long long)(b.pair_off[x] + pp) * kAdjFields * st + mol;
+    PairAdj adj;
+    if (b.det) { adj.P[0] = det_value(padj, a); adj.P[1] = det_value(padj, a + st); adj.P[2] = det_value(padj, a + 2 * st); adj.g = det_value(padj, a + 3 * st); adj.K = det_value(padj, a + 4 * st); }
+    else { adj.P[0] = padj[a]; adj.P[1] = padj[a + st]; adj.P[2] = padj[a + 2 * st]; adj.g = padj[a + 3 * st]; adj.K = padj[a + 4 * st]; }
     double ab = 0, bb = 0, cab = 0, cbb = 0;
     pair_backward(al[p], cn[p], xyz + 3 * i, b.f_type[i], al[q], cn[q], xyz + 3 * j, b.f_type[j], adj, 0.0, 0.0, &ab, &bb, &cab, &cbb,
                   Ab, Bb);
-    atomicAdd(ga + (size_t)mol * b.nprim + p, ab); atomicAdd(ga + (size_t)mol * b.nprim + q, bb);
-    atomicAdd(gc + (size_t)mol * b.nprim + p, cab); atomicAdd(gc + (size_t)mol * b.nprim + q, cbb);
+    acc_add(ga, (long long)mol * b.nprim + p, ab, b.det); acc_add(ga, (long long)mol * b.nprim + q, bb, b.det);
+    acc_add(gc, (long long)mol * b.nprim + p, cab, b.det); acc_add(gc, (long long)mol * b.nprim + q, cbb, b.det);
   }
-  if (b.f_type[i] > 0) Ab[b.f_type[i] - 1] -= pasum[((size_t)x * 2 + 0) * st + mol];
-  if (b.f_type[j] > 0) Bb[b.f_type[j] - 1] -= pasum[((size_t)x * 2 + 1) * st + mol];
-  double* g = gx + (size_t)mol * b.N * 3;
+  const long long pa = ((long long)x * 2 + 0) * st + mol, pb = ((long long)x * 2 + 1) * st + mol;
+  if (b.f_type[i] > 0) Ab[b.f_type[i] - 1] -= b.det ? det_value(pasum, pa) : pasum[pa];
+  if (b.f_type[j] > 0) Bb[b.f_type[j] - 1] -= b.det ? det_value(pasum, pb) : pasum[pb];
+  const long long g = (long long)mol * b.N * 3;
 #pragma unroll
-  for (int cdir = 0; cdir < 3; ++cdir) { atomicAdd(g + 3 * i + cdir, Ab[cdir]); atomicAdd(g + 3 * j + cdir, Bb[cdir]); }
+  for (int cdir = 0; cdir < 3; ++cdir) { acc_add(gx, g + 3 * i + cdir, Ab[cdir], b.det); acc_add(gx, g + 3 * j + cdir, Bb[cdir], b.det); }
 }
 
 // Sbar : dS + Hbar : d(T+V), one thread per (primitive-pair record, molecule), 10-direction duals
@@ -547,10 +551,10 @@ __global__ void kb_one_electron_grad(BatchDev b, const double* __restrict__ Sbar
   double g[10];
 #pragma unroll
   for (int c = 0; c < 10; ++c) g[c] = ws * Sv.d[c] + wh * (Tv.d[c] + Vv.d[c]);
-  double* gam = ga + (size_t)mol * b.nprim; double* gcm = gc + (size_t)mol * b.nprim; double* gxm = gx + (size_t)mol * n * 3;
-  atomicAdd(gam + p, g[0]); atomicAdd(gam + q, g[1]); atomicAdd(gcm + p, g[2]); atomicAdd(gcm + q, g[3]);
+  const long long gam = (long long)mol * b.nprim, gxm = (long long)mol * n * 3;
+  acc_add(ga, gam + p, g[0], b.det); acc_add(ga, gam + q, g[1], b.det); acc_add(gc, gam + p, g[2], b.det); acc_add(gc, gam + q, g[3], b.det);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { atomicAdd(gxm + 3 * i + c, g[4 + c]); atomicAdd(gxm + 3 * j + c, g[7 + c]); }
+  for (int c = 0; c < 3; ++c) { acc_add(gx, gxm + 3 * i + c, g[4 + c], b.det); acc_add(gx, gxm + 3 * j + c, g[7 + c], b.det); }
 }
 
 // normalisation adjoint (gc: normalised -> raw, ga +=) and d/d ln(alpha): one thread per (function, molecule)
@@ -664,10 +668,14 @@ int launch_batch_scf(cudaStream_t st, const BatchDev& b, const double* S, const 
   DQB_LAUNCHED();
   return 0;
 }
-void launch_batch_grad_finish(cudaStream_t st, const BatchDev& b, int log_alpha, const double* padj, const double* pasum, const double* Sbar,
-                              const double* Hbar, double* ga, double* gc, double* gx, double* graw) {
+// ga, gc, gx: accumulators (limb pairs when b.det)
+void launch_batch_grad_accumulate(cudaStream_t st, const BatchDev& b, const double* padj, const double* pasum, const double* Sbar,
+                                  const double* Hbar, double* ga, double* gc, double* gx) {
   kb_pair_bwd<<<cdivb((long long)b.M * b.nmol, 64), 64, 0, st>>>(b, padj, pasum, ga, gc, gx); DQB_LAUNCHED();
   kb_one_electron_grad<<<cdivb((long long)b.nrec * b.nmol, 64), 64, 0, st>>>(b, Sbar, Hbar, ga, gc, gx); DQB_LAUNCHED();
+}
+// ga, gc: doubles
+void launch_batch_grad_finish(cudaStream_t st, const BatchDev& b, int log_alpha, double* ga, const double* gc, double* graw) {
   kb_finish<<<cdivb((long long)b.N * b.nmol, 128), 128, 0, st>>>(b, log_alpha, ga, gc, graw); DQB_LAUNCHED();
 }
 

@@ -5,7 +5,7 @@
 //   k_one_electron(+_grad)          S, T, V and their parameter gradient                (Integrals.py:10-188)
 //   k_eri_tiles<class>              contracted ERIs, one 256-quartet tile per CTA       (Integrals.py:190-401)
 //   k_scatter_packed                tile store -> the reference's packed Eri_vec order  (Tools.py:17-51)
-//   k_jk_chunks                     J/K contraction of the stored tiles with D          (Energy.py:29-38)
+//   k_jk_cols                       J/K contraction of the stored tiles with D          (Energy.py:29-38)
 //   k_eri_grad_chunks<class>        sum Gamma_ijkl d(ij|kl)/d(pair fields), reverse mode, chunks of tiles sharing the ket
 //   k_pair_bwd                      pair-field adjoints -> exponents, coefficients, centres
 //   k_gemm, k_eigh_jacobi, small elementwise kernels for the SCF and its reverse sweep (Energy.py:138-195, Eigen.py)
@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "dq_layout.h"
@@ -28,9 +30,26 @@ static thread_local long long g_launches = 0;   // kernels launched by this host
 long long launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
+// one "Boys loop ran out of terms" flag per device, shared by every host thread driving that device
+int* boys_fail_flag() {
+  static std::mutex mu;
+  static std::map<int, int*> flags;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  int*& f = flags[dev];
+  if (!f) {
+    if (cudaMalloc(&f, sizeof(int)) != cudaSuccess) { f = nullptr; return nullptr; }
+    cudaMemset(f, 0, sizeof(int));
+  }
+  return f;
+}
+
 int upload_boys_constants() {
   BoysConst h;
   boys_const_init(&h);
+  h.fail = boys_fail_flag();
+  if (!h.fail) return 1;
   return (int)cudaMemcpyToSymbol(c_boys, &h, sizeof(h));
 }
 
@@ -182,10 +201,12 @@ __global__ void k_one_electron_grad(SystemDev s, int kmax, const double* __restr
   double g[10];
 #pragma unroll
   for (int c = 0; c < 10; ++c) g[c] = ws * Sv.d[c] + wh * (Tv.d[c] + Vv.d[c]);
-  atomicAdd(g_alpha + p, g[0]); atomicAdd(g_alpha + q, g[1]);
-  atomicAdd(g_coef + p, g[2]); atomicAdd(g_coef + q, g[3]);
+  // g_alpha, g_coef, g_xyz are three windows of ONE accumulator buffer (limb pairs in fixed-point mode): index from g_alpha
+  const long long oc = g_coef - g_alpha, ox = g_xyz - g_alpha;
+  acc_add(g_alpha, p, g[0], s.det); acc_add(g_alpha, q, g[1], s.det);
+  acc_add(g_alpha, oc + p, g[2], s.det); acc_add(g_alpha, oc + q, g[3], s.det);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { atomicAdd(g_xyz + 3 * i + c, g[4 + c]); atomicAdd(g_xyz + 3 * j + c, g[7 + c]); }
+  for (int c = 0; c < 3; ++c) { acc_add(g_alpha, ox + 3 * i + c, g[4 + c], s.det); acc_add(g_alpha, ox + 3 * j + c, g[7 + c], s.det); }
 }
 
 // =============================================================================================
@@ -424,109 +445,9 @@ __global__ void __launch_bounds__(256) k_scatter_packed(const Tile* __restrict__
 // uniformly (final J: upper block triangle mirrored; final K = Kacc + Kacc^T; DESIGN.md "Fock build").
 struct JkDesc { int sK, sL; short nK, nL; unsigned char same_bp, dKL, skip, pad_; };   // ket block pair of one tile, 16 bytes
 
-__global__ void __launch_bounds__(256) k_jk_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
-                                                   const double* __restrict__ store, const double* __restrict__ D,
-                                                   double* __restrict__ Jacc, double* __restrict__ Kacc) {
-  extern __shared__ double sm[];
-  const int n = s.N, tid = threadIdx.x;
-  const int ns = n | 1;                 // odd row stride: the 4 rows of a strip fall into different banks
-  double* dstrip = sm;                  // [8][ns]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
-  double* kstrip = sm + 8 * ns;         // [8][ns]
-  double* sv = kstrip + 8 * ns;         // [2][16*17]
-  double* sdij = sv + 2 * 16 * 17;      // [16]
-  JkDesc* desc = (JkDesc*)(sdij + 16);  // [256] ket descriptors of the chunk (breaks the tile -> block pair -> D load chain)
-  const int2 ch = chunks[blockIdx.x];
-  const int bp1 = tiles[ch.x].bp1;
-  const BlockPair b1 = s.bp[bp1];
-  const bool dIJ = b1.bI == b1.bJ;
-  if (tid < ch.y) {
-    const int bp2 = tiles[ch.x + tid].bp2;
-    const BlockPair b2 = s.bp[bp2];
-    JkDesc d; d.sK = b2.sI; d.sL = b2.sJ; d.nK = (short)b2.nI; d.nL = (short)b2.nJ; d.same_bp = bp2 == bp1; d.dKL = b2.bI == b2.bJ;
-    d.skip = tile_screened(s, tiles[ch.x + tid]); d.pad_ = 0;
-    desc[tid] = d;
-  }
-  for (int x = tid; x < 8 * ns; x += 256) {
-    const int row = x / ns, col = x - row * ns, r = row & 3;
-    const bool isJ = row >= 4;
-    const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
-    dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
-    kstrip[x] = 0.0;
-  }
-  const int il = tid >> 6, jl = (tid >> 4) & 3, kl = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
-  if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
-  double jacc = 0.0;
-  __syncthreads();
-  // software pipeline, depth 2: ERI value and D_kl of tiles t+1, t+2 are in flight while tile t is digested
-  auto load_dkl = [&](int t) {
-    const JkDesc d = desc[t];
-    return (!d.skip && kl < d.nK && ll < d.nL) ? D[(d.sK + kl) * n + d.sL + ll] : 0.0;
-  };
-  auto load_v = [&](int t) { return desc[t].skip ? 0.0 : store[(long long)(ch.x + t) * kTile + tid]; };   // screened tiles are not read
-  double v1 = load_v(0), d1 = load_dkl(0), v2 = 0.0, d2 = 0.0;
-  if (ch.y > 1) { v2 = load_v(1); d2 = load_dkl(1); }
-  int nproc = 0;                        // processed (non-screened) tiles: selects the sv buffer
-  for (int t = 0; t < ch.y; ++t) {
-    const JkDesc b2 = desc[t];
-    const double v = v1, dkl = d1;
-    v1 = v2; d1 = d2;
-    if (t + 2 < ch.y) { v2 = load_v(t + 2); d2 = load_dkl(t + 2); }
-    if (b2.skip) continue;
-    const bool dKL = b2.dKL != 0;
-    const double wS = b2.same_bp ? 0.5 : 1.0;
-    jacc += (wS * (dKL ? 1.0 : 2.0)) * dkl * v;
-    double* svb = sv + (nproc & 1) * (16 * 17);
-    ++nproc;
-    svb[bl * 17 + kt] = v;
-    __syncthreads();
-    // digest by warps 0-1 only; the other warps run ahead into the next tile (double-buffered sv).  Measured: spreading
-    // the 1536 MACs over all 8 warps is slower (2.6 ms vs 2.2 ms per build) - the tile loop is bound by instruction issue
-    // and the stream of 2 KB tiles, not by the latency of these two warps.
-    if (tid < 16) {                      // J[k,l] (lane = kl*4+ll)
-      double acc = 0.0;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc += sdij[q] * svb[q * 17 + tid];
-      const int k = tid >> 2, l = tid & 3;
-      if (k < b2.nK && l < b2.nL && acc != 0.0) atomicAdd(Jacc + (b2.sK + k) * n + b2.sL + l, wS * (dIJ ? 1.0 : 2.0) * acc);
-    } else if (tid >= 32 && tid < 64) {  // K strips: thread (strip, r, x) owns K[strip row r, k = x] and K[strip row r, l = x]
-      const int u = tid - 32, strip = u >> 4, r = (u >> 2) & 3, x = u & 3;
-      const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
-      // strip 0 (rows of I): K[i,k] += sum_{j,l} D[j,l] v[i j k l];  K[i,l] += sum_{j,k} D[j,k] v
-      // strip 1 (rows of J): K[j,k] += sum_{i,l} D[i,l] v[i j k l];  K[j,l] += sum_{i,k} D[i,k] v
-      const double* dother = dstrip + (strip == 0 ? 4 : 0) * ns;   // D rows of the OTHER bra block
-      double a1 = 0.0, a2 = 0.0;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {        // o: index inside the other bra block
-        const int brow = strip == 0 ? (r * 4 + o) : (o * 4 + r);   // bra lane il*4+jl
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          a1 += dother[o * ns + b2.sL + y] * svb[brow * 17 + x * 4 + y];   // k = x, l = y
-          a2 += dother[o * ns + b2.sK + y] * svb[brow * 17 + y * 4 + x];   // k = y, l = x
-        }
-      }
-      double* ks = kstrip + (strip * 4 + r) * ns;     // K == L: the same thread owns both updates, no race
-      if (x < b2.nK) ks[b2.sK + x] += w * a1;
-      if (x < b2.nL) ks[b2.sL + x] += w * a2;
-    }
-  }
-  // J[i,j]: reduce the 16 ket lanes
-#pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) jacc += __shfl_xor_sync(0xffffffffu, jacc, o);
-  if (kt == 0 && il < b1.nI && jl < b1.nJ && jacc != 0.0) atomicAdd(Jacc + (b1.sI + il) * n + b1.sJ + jl, jacc);
-  __syncthreads();
-  for (int x = tid; x < 8 * ns; x += 256) {
-    const double val = kstrip[x];
-    if (val != 0.0) {
-      const int row = x / ns, col = x - row * ns, r = row & 3;
-      atomicAdd(Kacc + ((row >= 4 ? b1.sJ : b1.sI) + r) * n + col, val);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// J/K contraction, column-owner form (the default).  Same chunks, same strips, same weights as k_jk_chunks above, but no
-// per-tile CTA barrier and no digest warps: every WARP streams its own share of the chunk, two tiles per step, one LANE per
-// ket pair (k,l) of a tile.  The lane reads the 16 bra-pair values of its column (coalesced: 16 lanes x 8 B per row of
+// J/K contraction, column-owner form: no per-tile CTA barrier, every WARP streams its own share of the chunk, two tiles
+// per step, one LANE per ket pair (k,l) of a tile.  The lane reads the 16 bra-pair values of its column (coalesced: 16 lanes x 8 B per row of
 // the tile) and owns them in registers:
 //   J[k,l]   = sum_ij D_ij v            complete in the lane: one global atomic
 //   J[i,j]  += D_kl v                   16 register accumulators kept for the whole chunk, reduced once at the end
@@ -555,9 +476,11 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
   extern __shared__ double sm[];
   const int n = s.N, tid = threadIdx.x;
   const int ns = n | 1;
+  const int det = s.det;
+  const int nk = (det ? 16 : 8) * ns;   // K strips: doubles, or pairs of integer limbs (fixed-point accumulation)
   double* dstrip = sm;                  // [8][ns]  rows 0-3: D[I rows, :], rows 4-7: D[J rows, :]
-  double* kstrip = sm + 8 * ns;         // [8][ns]
-  double* sdij = kstrip + 8 * ns;       // [16]
+  double* kstrip = sm + 8 * ns;         // [8][ns] (x 2 limbs)
+  double* sdij = kstrip + nk;           // [16]
   JkDesc* desc = (JkDesc*)(sdij + 16);  // [256]
   const int2 ch = chunks[blockIdx.x];
   const int bp1 = tiles[ch.x].bp1;
@@ -575,8 +498,8 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
     const bool isJ = row >= 4;
     const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
     dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
-    kstrip[x] = 0.0;
   }
+  for (int x = tid; x < nk; x += 256) kstrip[x] = 0.0;        // (all-zero bits are the integer 0 as well)
   if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
   __syncthreads();
 
@@ -603,7 +526,7 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
     double jkl = 0.0;
 #pragma unroll
     for (int q = 0; q < 16; ++q) { jacc[q] = fma(jw, v[q], jacc[q]); jkl = fma(sdij[q], v[q], jkl); }
-    if (inb && jkl != 0.0) atomicAdd(Jacc + (d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl);
+    if (inb && jkl != 0.0) acc_add(Jacc, (long long)(d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl, det);
     // exchange: D of the OTHER bra block at the lane's ket column / row
     const int ck = d.sK + k, cl = d.sL + l;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
@@ -628,12 +551,12 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
     const double kjl = reduce_scatter4(e[0], e[1], e[2], e[3], k >> 1, k & 1, 8, 4);     // j = k
     if (act) {
       if (k < d.nK) {
-        if (kik != 0.0) atomicAdd(kstrip + l * ns + ck, w * kik);
-        if (kjk != 0.0) atomicAdd(kstrip + (4 + l) * ns + ck, w * kjk);
+        if (kik != 0.0) acc_add(kstrip, l * ns + ck, w * kik, det);
+        if (kjk != 0.0) acc_add(kstrip, (4 + l) * ns + ck, w * kjk, det);
       }
       if (l < d.nL) {
-        if (kil != 0.0) atomicAdd(kstrip + k * ns + cl, w * kil);
-        if (kjl != 0.0) atomicAdd(kstrip + (4 + k) * ns + cl, w * kjl);
+        if (kil != 0.0) acc_add(kstrip, k * ns + cl, w * kil, det);
+        if (kjl != 0.0) acc_add(kstrip, (4 + k) * ns + cl, w * kjl, det);
       }
     }
   }
@@ -646,16 +569,376 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < 16; ++q)
-      if ((q >> 2) < b1.nI && (q & 3) < b1.nJ && jacc[q] != 0.0) atomicAdd(Jacc + (b1.sI + (q >> 2)) * n + b1.sJ + (q & 3), jacc[q]);
+      if ((q >> 2) < b1.nI && (q & 3) < b1.nJ && jacc[q] != 0.0) acc_add(Jacc, (long long)(b1.sI + (q >> 2)) * n + b1.sJ + (q & 3), jacc[q], det);
   }
   __syncthreads();
   for (int x = tid; x < 8 * ns; x += 256) {
-    const double val = kstrip[x];
-    if (val != 0.0) {
-      const int row = x / ns, col = x - row * ns, r = row & 3;
-      atomicAdd(Kacc + ((row >= 4 ? b1.sJ : b1.sI) + r) * n + col, val);
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const long long g = (long long)((row >= 4 ? b1.sJ : b1.sI) + r) * n + col;
+    if (det) {          // the strip's limbs go to the global limbs as they are: integer adds, nothing is re-rounded
+      const unsigned long long* sp = (const unsigned long long*)kstrip + 2 * x;
+      unsigned long long* gp = (unsigned long long*)Kacc + 2 * g;
+      if (sp[0]) atomicAdd(gp, sp[0]);
+      if (sp[1]) atomicAdd(gp + 1, sp[1]);
+    } else {
+      const double val = kstrip[x];
+      if (val != 0.0) atomicAdd(Kacc + g, val);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// J/K contraction, bulk-async form (the default): the same chunks, strips, lane math and weights as k_jk_cols, but the tiles
+// do not go through the register file on their way in.  Every WARP owns a ring of kJkSlots slots of two tiles (4 KB) in
+// shared memory; lane 0 arms the slot's mbarrier with the byte count (mbarrier.arrive.expect_tx) and issues ONE 1-D TMA
+// copy per slot (cp.async.bulk.shared::cluster.global, evict-first L2 policy: the 2.6 GB tile stream is read once per
+// build and must not push D and the strips out of L2); the warp waits on the barrier's phase bit, pulls its 16 values per
+// lane out of the slot, and lane 0 re-arms the slot with the copy of the stage kJkSlots ahead BEFORE the 96 FMAs of the
+// current one.  No CTA barrier and no cross-warp hand-over inside a chunk: a slot is produced and consumed by one warp, so
+// "slot free" is a __syncwarp.  16 warps per SM keep 16 x kJkSlots x 4 KB = 128 KB of copies in flight per SM, against the
+// ~45 KB that 6.5 TB/s x ~1 us of loaded HBM latency / 148 SMs asks for.
+// ---------------------------------------------------------------------------------------------
+constexpr int kJkSlots = 2;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DQ_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DQ_DONE_%=;\n"
+      "bra DQ_WAIT_%=;\n"
+      "DQ_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// one 1-D bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) k_jk_stream(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
+                                                      const double* __restrict__ store, const double* __restrict__ D,
+                                                      double* __restrict__ Jacc, double* __restrict__ Kacc) {
+  extern __shared__ __align__(128) double sm[];
+  const int n = s.N, tid = threadIdx.x;
+  const int ns = n | 1;
+  const int det = s.det;
+  const int nk = (det ? 16 : 8) * ns;
+  double* ring = sm;                                        // [8 warps][kJkSlots][2 tiles][256]  (first: 128-byte aligned)
+  unsigned long long* bars = (unsigned long long*)(ring + 8 * kJkSlots * 2 * kTile);      // [8][kJkSlots]
+  JkDesc* desc = (JkDesc*)(bars + 8 * kJkSlots);            // [256]
+  double* sdij = (double*)(desc + 256);                     // [16]
+  double* dstrip = sdij + 16;                               // [8][ns]
+  double* kstrip = dstrip + 8 * ns;                         // [8][ns] (x 2 limbs)
+  const int2 ch = chunks[blockIdx.x];
+  const int bp1 = tiles[ch.x].bp1;
+  const BlockPair b1 = s.bp[bp1];
+  const bool dIJ = b1.bI == b1.bJ;
+  const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, kl = lane & 15, k = kl >> 2, l = kl & 3;
+  // stages of this warp: j = warp + 8 i, tiles 2j and 2j+1 of the chunk
+  const int nstage = (ch.y + 1) >> 1;
+  const int ni = nstage > warp ? (nstage - warp + 7) >> 3 : 0;
+  double* myring = ring + (size_t)warp * kJkSlots * 2 * kTile;
+  unsigned long long* mybar = bars + warp * kJkSlots;
+  const unsigned long long pol = l2_evict_first_policy();
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < kJkSlots; ++r) mbar_init(mybar + r, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // make the initialised barriers visible to the async proxy
+  }
+  __syncwarp();
+  auto issue = [&](int i) {          // lane 0: the copy of this warp's stage i into slot i % kJkSlots
+    const int j = warp + 8 * i;
+    const unsigned bytes = (unsigned)(min(2, ch.y - 2 * j) * kTile * sizeof(double));
+    unsigned long long* bar = mybar + (i % kJkSlots);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(myring + (size_t)(i % kJkSlots) * 2 * kTile, store + (long long)(ch.x + 2 * j) * kTile, bytes, bar, pol);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < kJkSlots; ++r) if (r < ni) issue(r);
+  }
+  // while the first copies fly: ket descriptors, D strips, zeroed K strips
+  if (tid < ch.y) {
+    const int bp2 = tiles[ch.x + tid].bp2;
+    const BlockPair b2 = s.bp[bp2];
+    JkDesc d; d.sK = b2.sI; d.sL = b2.sJ; d.nK = (short)b2.nI; d.nL = (short)b2.nJ; d.same_bp = bp2 == bp1; d.dKL = b2.bI == b2.bJ;
+    d.skip = tile_screened(s, tiles[ch.x + tid]); d.pad_ = 0;
+    desc[tid] = d;
+  }
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const bool isJ = row >= 4;
+    const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
+    dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
+  }
+  for (int x = tid; x < nk; x += 256) kstrip[x] = 0.0;
+  if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
+  __syncthreads();
+
+  double jacc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) jacc[q] = 0.0;
+  for (int i = 0; i < ni; ++i) {
+    const int t = 2 * (warp + 8 * i) + h;
+    const JkDesc d = desc[t < ch.y ? t : ch.y - 1];
+    const bool act = t < ch.y && !d.skip;
+    const bool inb = act && k < d.nK && l < d.nL;
+    const double dkl = inb ? D[(d.sK + k) * n + d.sL + l] : 0.0;
+    const int slot = i % kJkSlots;
+    mbar_wait(mybar + slot, (unsigned)((i / kJkSlots) & 1));
+    double v[16];
+    const double* src = myring + (size_t)slot * 2 * kTile + h * kTile + kl;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = act ? src[q * 16] : 0.0;
+    __syncwarp();                                   // every lane has its values: the slot is free
+    if (lane == 0 && i + kJkSlots < ni) issue(i + kJkSlots);
+    const double wS = d.same_bp ? 0.5 : 1.0;
+    const bool dKL = d.dKL != 0;
+    const double jw = wS * (dKL ? 1.0 : 2.0) * dkl;
+    double jkl = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { jacc[q] = fma(jw, v[q], jacc[q]); jkl = fma(sdij[q], v[q], jkl); }
+    if (inb && jkl != 0.0) acc_add(Jacc, (long long)(d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl, det);
+    const int ck = d.sK + k, cl = d.sL + l;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) { a[ii] = fma(dJl, v[ii * 4 + j], a[ii]); b[ii] = fma(dJk, v[ii * 4 + j], b[ii]); }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const double dIl = dstrip[ii * ns + cl], dIk = dstrip[ii * ns + ck];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[ii * 4 + j], c[j]); e[j] = fma(dIk, v[ii * 4 + j], e[j]); }
+    }
+    const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
+    const double kik = reduce_scatter4(a[0], a[1], a[2], a[3], l >> 1, l & 1, 2, 1);
+    const double kil = reduce_scatter4(b[0], b[1], b[2], b[3], k >> 1, k & 1, 8, 4);
+    const double kjk = reduce_scatter4(c[0], c[1], c[2], c[3], l >> 1, l & 1, 2, 1);
+    const double kjl = reduce_scatter4(e[0], e[1], e[2], e[3], k >> 1, k & 1, 8, 4);
+    if (act) {
+      if (k < d.nK) {
+        if (kik != 0.0) acc_add(kstrip, l * ns + ck, w * kik, det);
+        if (kjk != 0.0) acc_add(kstrip, (4 + l) * ns + ck, w * kjk, det);
+      }
+      if (l < d.nL) {
+        if (kil != 0.0) acc_add(kstrip, k * ns + cl, w * kil, det);
+        if (kjl != 0.0) acc_add(kstrip, (4 + k) * ns + cl, w * kjl, det);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) jacc[q] += __shfl_xor_sync(0xffffffffu, jacc[q], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if ((q >> 2) < b1.nI && (q & 3) < b1.nJ && jacc[q] != 0.0) acc_add(Jacc, (long long)(b1.sI + (q >> 2)) * n + b1.sJ + (q & 3), jacc[q], det);
+  }
+  __syncthreads();
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const long long g = (long long)((row >= 4 ? b1.sJ : b1.sI) + r) * n + col;
+    if (det) {
+      const unsigned long long* sp = (const unsigned long long*)kstrip + 2 * x;
+      unsigned long long* gp = (unsigned long long*)Kacc + 2 * g;
+      if (sp[0]) atomicAdd(gp, sp[0]);
+      if (sp[1]) atomicAdd(gp + 1, sp[1]);
+    } else {
+      const double val = kstrip[x];
+      if (val != 0.0) atomicAdd(Kacc + g, val);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Integral-direct J/K (dq_options.jk_mode = 2; Energy.py:29-38 with no stored Eri vector): ONE kernel per angular class
+// evaluates the tiles of a chunk (same bra block pair) exactly as k_eri_tiles does and contracts each tile's 256 ERIs with
+// D right after its primitive loop - the tile never leaves the SM.  The thread of quartet (ij|kl) drops its value into a
+// double-buffered 2 KB shared-memory tile; after the next CTA barrier (the one the ket staging of the following tile needs
+// anyway) 16 lanes of warp 0 run the lane math of k_jk_cols on it - lane = ket pair for J[kl] and the four exchange pieces,
+// lane = bra pair for J[ij] - while the other warps already stage the next ket: ~150 instructions of one half-warp per
+// tile against 256 x 81 primitive quartets.  The bra records, D[I,:], D[J,:] and the K row strips are staged once per chunk.
+// ---------------------------------------------------------------------------------------------
+template <bool LA, bool LB, bool LC, bool LD, bool ZS>
+__global__ void __launch_bounds__(256) k_jk_direct(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
+                                                   const double* __restrict__ pd, const double* __restrict__ D,
+                                                   double* __restrict__ Jacc, double* __restrict__ Kacc, int kkmax) {
+  extern __shared__ double sm[];
+  const int n = s.N, tid = threadIdx.x;
+  const int ns = n | 1;
+  const int det = s.det;
+  const int nk = (det ? 16 : 8) * ns;
+  double* sbra = sm;                                   // [kkmax * 8 * 16]
+  double* sket = sbra + kkmax * kPairFields * 16;      // [kkmax * 8 * 16]
+  double* sv = sket + kkmax * kPairFields * 16;        // [2][16 * 17]  the tile being digested / the tile being filled
+  double* sdij = sv + 2 * 16 * 17;                     // [16]
+  double* dstrip = sdij + 16;                          // [8][ns]
+  double* kstrip = dstrip + 8 * ns;                    // [8][ns] (x 2 limbs)
+  const int2 ch = chunks[blockIdx.x];
+  const int bp1 = tiles[ch.x].bp1;
+  const BlockPair b1 = s.bp[bp1];
+  const bool dIJ = b1.bI == b1.bJ;
+  const int il = tid >> 6, jl = (tid >> 4) & 3, kl4 = (tid >> 2) & 3, ll = tid & 3, bl = tid >> 4, kt = tid & 15;
+  {
+    const double* gb = pd + b1.off * 16;
+    for (int x = tid; x < b1.KK * kPairFields * 16; x += 256) sbra[x] = gb[x];
+  }
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const bool isJ = row >= 4;
+    const bool ok = r < (isJ ? b1.nJ : b1.nI) && col < n;
+    dstrip[x] = ok ? D[((isJ ? b1.sJ : b1.sI) + r) * n + col] : 0.0;
+  }
+  for (int x = tid; x < nk; x += 256) kstrip[x] = 0.0;
+  if (tid < 16) sdij[tid] = ((tid >> 2) < b1.nI && (tid & 3) < b1.nJ) ? D[(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3)] : 0.0;
+  const int ia = b1.axI, ib = b1.axJ;
+  double jij = 0.0;                 // lanes 0-15 of warp 0: J[i,j] of bra pair `tid`, accumulated over the chunk
+
+  // digest of one finished tile: the whole warp 0 calls it (the shuffles name all 32 lanes); lanes 16-31 mirror lanes 0-15 and
+  // add nothing.  lane = ket pair kl for J[kl] and the exchange pieces, then lane = bra pair ij for J[ij].
+  auto digest = [&](int t) {
+    const Tile tl = tiles[ch.x + t];
+    if (tile_screened(s, tl)) return;
+    const BlockPair b2 = s.bp[tl.bp2];
+    const double* svb = sv + (t & 1) * (16 * 17);
+    const int c16 = tid & 15;
+    const bool on = tid < 16;
+    const int k = c16 >> 2, l = c16 & 3;
+    const bool inb = k < b2.nI && l < b2.nJ;
+    const bool dKL = b2.bI == b2.bJ;
+    const double wS = tl.bp2 == bp1 ? 0.5 : 1.0;
+    const double dkl = inb ? D[(b2.sI + k) * n + b2.sJ + l] : 0.0;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = svb[q * 17 + c16];
+    double jkl = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) jkl = fma(sdij[q], v[q], jkl);
+    if (on && inb && jkl != 0.0) acc_add(Jacc, (long long)(b2.sI + k) * n + b2.sJ + l, wS * (dIJ ? 1.0 : 2.0) * jkl, det);
+    // J[i,j] of bra pair c16: sum over the ket pairs, the weighted D_kl of lane x fetched by shuffle
+    {
+      const double jw = wS * (dKL ? 1.0 : 2.0) * dkl;
+      double acc = 0.0;
+#pragma unroll
+      for (int x = 0; x < 16; ++x) acc = fma(__shfl_sync(0xffffffffu, jw, x), svb[c16 * 17 + x], acc);
+      jij += acc;
+    }
+    const int ck = b2.sI + k, cl = b2.sJ + l;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = fma(dJl, v[i * 4 + j], a[i]); b[i] = fma(dJk, v[i * 4 + j], b[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double dIl = dstrip[i * ns + cl], dIk = dstrip[i * ns + ck];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[i * 4 + j], c[j]); e[j] = fma(dIk, v[i * 4 + j], e[j]); }
+    }
+    const double w = wS * (dIJ ? 0.5 : 1.0) * (dKL ? 0.5 : 1.0);
+    const double kik = reduce_scatter4(a[0], a[1], a[2], a[3], l >> 1, l & 1, 2, 1);
+    const double kil = reduce_scatter4(b[0], b[1], b[2], b[3], k >> 1, k & 1, 8, 4);
+    const double kjk = reduce_scatter4(c[0], c[1], c[2], c[3], l >> 1, l & 1, 2, 1);
+    const double kjl = reduce_scatter4(e[0], e[1], e[2], e[3], k >> 1, k & 1, 8, 4);
+    if (on && k < b2.nI) {
+      if (kik != 0.0) acc_add(kstrip, l * ns + ck, w * kik, det);
+      if (kjk != 0.0) acc_add(kstrip, (4 + l) * ns + ck, w * kjk, det);
+    }
+    if (on && l < b2.nJ) {
+      if (kil != 0.0) acc_add(kstrip, k * ns + cl, w * kil, det);
+      if (kjl != 0.0) acc_add(kstrip, (4 + k) * ns + cl, w * kjl, det);
+    }
+  };
+
+  for (int t = 0; t < ch.y; ++t) {
+    const Tile tl = tiles[ch.x + t];
+    const BlockPair b2 = s.bp[tl.bp2];
+    __syncthreads();                  // tile t-1: primitive loops done (sket free), its 256 values are in sv[(t-1) & 1]
+    if (t > 0 && tid < 32) digest(t - 1);      // warp 0; the other warps go on to stage the next ket
+    if (tile_screened(s, tl)) {       // CTA-uniform
+      if (tid == 0) atomicAdd(s.skipped, 1ULL);
+      continue;
+    }
+    {
+      const double* gk = pd + b2.off * 16;
+      for (int x = tid; x < b2.KK * kPairFields * 16; x += 256) sket[x] = gk[x];
+    }
+    __syncthreads();
+    double v = 0.0;
+    if (il < b1.nI && jl < b1.nJ && kl4 < b2.nI && ll < b2.nJ) {
+      const int ic = b2.axI, id = b2.axJ;
+      const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+      for (int pb = 0; pb < b1.KK; ++pb) {
+        const double* brec = sbra + pb * kPairFields * 16;
+        const PairPrim bra = load_pair(brec, bl);
+        if (ZS && bra.K == 0.0) continue;
+        double bs[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LA) bs[0] = brec[ia * 16 + bl];
+        if (LB) bs[1] = brec[ib * 16 + bl];
+        if (LC) bs[2] = brec[ic * 16 + bl];
+        if (LD) bs[3] = brec[id * 16 + bl];
+        for (int pk = 0; pk < b2.KK; ++pk) {
+          const double* krec = sket + pk * kPairFields * 16;
+          const PairPrim ket = load_pair(krec, kt);
+          if (ZS && ket.K == 0.0) continue;
+          double ds[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) ds[0] = bs[0] - krec[ia * 16 + kt];
+          if (LB) ds[1] = bs[1] - krec[ib * 16 + kt];
+          if (LC) ds[2] = bs[2] - krec[ic * 16 + kt];
+          if (LD) ds[3] = bs[3] - krec[id * 16 + kt];
+          v += prim_quartet<LA, LB, LC, LD, false>(bra, ket, ds, dl, c_boys, 0.0, nullptr);
+        }
+      }
+    }
+    sv[(t & 1) * (16 * 17) + bl * 17 + kt] = v;
+  }
+  __syncthreads();
+  if (tid < 32) digest(ch.y - 1);
+  if (tid < 16 && (tid >> 2) < b1.nI && (tid & 3) < b1.nJ && jij != 0.0)
+    acc_add(Jacc, (long long)(b1.sI + (tid >> 2)) * n + b1.sJ + (tid & 3), jij, det);
+  __syncthreads();
+  for (int x = tid; x < 8 * ns; x += 256) {
+    const int row = x / ns, col = x - row * ns, r = row & 3;
+    const long long g = (long long)((row >= 4 ? b1.sJ : b1.sI) + r) * n + col;
+    if (det) {
+      const unsigned long long* sp = (const unsigned long long*)kstrip + 2 * x;
+      unsigned long long* gp = (unsigned long long*)Kacc + 2 * g;
+      if (sp[0]) atomicAdd(gp, sp[0]);
+      if (sp[1]) atomicAdd(gp + 1, sp[1]);
+    } else {
+      const double val = kstrip[x];
+      if (val != 0.0) atomicAdd(Kacc + g, val);
+    }
+  }
+}
+
+// limb pairs -> doubles: out[i] = beta * out[i] + value(in, i)
+__global__ void k_det_finalize(long long n, const double* __restrict__ in, double* __restrict__ out, double beta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (beta != 0.0 ? beta * out[i] : 0.0) + det_value(in, i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -788,15 +1071,15 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         if (kt == 0) {
 #pragma unroll
           for (int f = 0; f < kAdjFields; ++f)
-            if (r[f] != 0.0) atomicAdd(padj + (off5b + (long long)pb * kAdjFields + f) * 16 + bl, r[f]);
+            if (r[f] != 0.0) acc_add(padj, (off5b + (long long)pb * kAdjFields + f) * 16 + bl, r[f], s.det);
         }
       }
       if (LA || LB) {
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) { pas += __shfl_xor_sync(0xffffffffu, pas, o); pbs += __shfl_xor_sync(0xffffffffu, pbs, o); }
         if (kt == 0) {
-          if (pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas);
-          if (pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs);
+          if (pas != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas, s.det);
+          if (pbs != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs, s.det);
         }
       }
     }
@@ -814,8 +1097,8 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
 #pragma unroll
       for (int b = 0; b < 16; ++b) sum += sacc[slot * 256 + b * 16 + kt];
       if (sum != 0.0) {
-        if (slot < kn * kAdjFields) atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + slot) * 16 + kt, sum);
-        else atomicAdd(pasum + ((long long)bp2 * 2 + (slot - kn * kAdjFields)) * 16 + kt, sum);
+        if (slot < kn * kAdjFields) acc_add(padj, (off5k + (long long)k0 * kAdjFields + slot) * 16 + kt, sum, s.det);
+        else acc_add(pasum, ((long long)bp2 * 2 + (slot - kn * kAdjFields)) * 16 + kt, sum, s.det);
       }
     }
     __syncthreads();
@@ -953,22 +1236,22 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
         if (LB) add3(ba.P, ib, bsl[1]);
         if (LC) add3(ba.P, ic, bsl[2]);
         if (LD) add3(ba.P, id, bsl[3]);
-        double* o = padj + (off5b + (long long)pb * kAdjFields) * 16 + bl;
-        if (ba.P[0] != 0.0) atomicAdd(o, ba.P[0]);
-        if (ba.P[1] != 0.0) atomicAdd(o + 16, ba.P[1]);
-        if (ba.P[2] != 0.0) atomicAdd(o + 32, ba.P[2]);
-        if (ba.g != 0.0) atomicAdd(o + 48, ba.g);
-        if (ba.K != 0.0) atomicAdd(o + 64, ba.K);
+        const long long o = (off5b + (long long)pb * kAdjFields) * 16 + bl;
+        if (ba.P[0] != 0.0) acc_add(padj, o, ba.P[0], s.det);
+        if (ba.P[1] != 0.0) acc_add(padj, o + 16, ba.P[1], s.det);
+        if (ba.P[2] != 0.0) acc_add(padj, o + 32, ba.P[2], s.det);
+        if (ba.g != 0.0) acc_add(padj, o + 48, ba.g, s.det);
+        if (ba.K != 0.0) acc_add(padj, o + 64, ba.K, s.det);
       }
       // this quartet's ket adjoints: flush the private slots and clear them for the next list entry
       for (int x = 0; x < kn * kAdjFields; ++x) {
         const double v = sacc[x * 256 + tid];
-        if (v != 0.0) { atomicAdd(padj + (off5k + (long long)k0 * kAdjFields + x) * 16 + kt, v); sacc[x * 256 + tid] = 0.0; }
+        if (v != 0.0) { acc_add(padj, (off5k + (long long)k0 * kAdjFields + x) * 16 + kt, v, s.det); sacc[x * 256 + tid] = 0.0; }
       }
-      if (LA && pas != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas);
-      if (LB && pbs != 0.0) atomicAdd(pasum + ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs);
-      if (LC && qcs != 0.0) atomicAdd(pasum + ((long long)bp2 * 2 + 0) * 16 + kt, qcs);
-      if (LD && qds != 0.0) atomicAdd(pasum + ((long long)bp2 * 2 + 1) * 16 + kt, qds);
+      if (LA && pas != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas, s.det);
+      if (LB && pbs != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs, s.det);
+      if (LC && qcs != 0.0) acc_add(pasum, ((long long)bp2 * 2 + 0) * 16 + kt, qcs, s.det);
+      if (LD && qds != 0.0) acc_add(pasum, ((long long)bp2 * 2 + 1) * 16 + kt, qds, s.det);
     }
   }
   if (s.zero_weight) {
@@ -1005,23 +1288,27 @@ __global__ void __launch_bounds__(128) k_pair_bwd(SystemDev s, const double* __r
   const int i = b.sI + il, j = b.sJ + jl;
   const long long off5 = b.off / kPairFields * kAdjFields;
   double Ab[3] = {0, 0, 0}, Bb[3] = {0, 0, 0};
+  const long long oc = g_coef - g_alpha, ox = g_xyz - g_alpha;     // windows of one accumulator buffer (see k_one_electron_grad)
   const int first = threadIdx.x >> 4;
   for (int pp = first; pp < b.KK; pp += blockDim.x >> 4) {
     const int p = s.f_off[i] + pp / b.KJ, q = s.f_off[j] + pp % b.KJ;
-    const double* a = padj + (off5 + (long long)pp * kAdjFields) * 16 + lane;
-    PairAdj adj; adj.P[0] = a[0]; adj.P[1] = a[16]; adj.P[2] = a[32]; adj.g = a[48]; adj.K = a[64];
+    const long long a = (off5 + (long long)pp * kAdjFields) * 16 + lane;
+    PairAdj adj;
+    if (s.det) { adj.P[0] = det_value(padj, a); adj.P[1] = det_value(padj, a + 16); adj.P[2] = det_value(padj, a + 32); adj.g = det_value(padj, a + 48); adj.K = det_value(padj, a + 64); }
+    else { adj.P[0] = padj[a]; adj.P[1] = padj[a + 16]; adj.P[2] = padj[a + 32]; adj.g = padj[a + 48]; adj.K = padj[a + 64]; }
     double ab = 0, bb = 0, cab = 0, cbb = 0;
     pair_backward(s.p_alpha[p], s.p_coef[p], s.f_xyz + 3 * i, s.f_type[i], s.p_alpha[q], s.p_coef[q], s.f_xyz + 3 * j,
                   s.f_type[j], adj, 0.0, 0.0, &ab, &bb, &cab, &cbb, Ab, Bb);
-    atomicAdd(g_alpha + p, ab); atomicAdd(g_alpha + q, bb);
-    atomicAdd(g_coef + p, cab); atomicAdd(g_coef + q, cbb);
+    acc_add(g_alpha, p, ab, s.det); acc_add(g_alpha, q, bb, s.det);
+    acc_add(g_alpha, oc + p, cab, s.det); acc_add(g_alpha, oc + q, cbb, s.det);
   }
   if (first == 0) {   // explicit centre dependence of (P-A)_a, (P-B)_b summed over the contraction
-    if (s.f_type[i] > 0) Ab[s.f_type[i] - 1] -= pasum[((long long)bpi * 2 + 0) * 16 + lane];
-    if (s.f_type[j] > 0) Bb[s.f_type[j] - 1] -= pasum[((long long)bpi * 2 + 1) * 16 + lane];
+    const long long pa = ((long long)bpi * 2 + 0) * 16 + lane, pb = ((long long)bpi * 2 + 1) * 16 + lane;
+    if (s.f_type[i] > 0) Ab[s.f_type[i] - 1] -= s.det ? det_value(pasum, pa) : pasum[pa];
+    if (s.f_type[j] > 0) Bb[s.f_type[j] - 1] -= s.det ? det_value(pasum, pb) : pasum[pb];
   }
 #pragma unroll
-  for (int x = 0; x < 3; ++x) { atomicAdd(g_xyz + 3 * i + x, Ab[x]); atomicAdd(g_xyz + 3 * j + x, Bb[x]); }
+  for (int x = 0; x < 3; ++x) { acc_add(g_alpha, ox + 3 * i + x, Ab[x], s.det); acc_add(g_alpha, ox + 3 * j + x, Bb[x], s.det); }
 }
 
 // =============================================================================================
@@ -1855,13 +2142,43 @@ void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const Sys
 void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* store,
                       const double* D, double* Jacc, double* Kacc) {
   if (nchunks <= 0) return;
-  const size_t smem = ((size_t)16 * (s.N | 1) + 2 * 16 * 17 + 16) * sizeof(double) + 256 * 16;
-  ensure_dynamic_smem(k_jk_chunks, smem);
-  static const bool old_kernel = getenv("DQ_JK_DIGEST") != nullptr;   // A/B switch: the per-tile digest kernel
-  if (old_kernel) { k_jk_chunks<<<nchunks, 256, smem, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED(); return; }
-  const size_t smem2 = ((size_t)16 * (s.N | 1) + 16) * sizeof(double) + 256 * 16;
+  const size_t smem2 = ((size_t)(s.det ? 24 : 16) * (s.N | 1) + 16) * sizeof(double) + 256 * 16;
+  const size_t smem3 = smem2 + (size_t)8 * kJkSlots * 2 * kTile * sizeof(double) + 8 * kJkSlots * sizeof(unsigned long long);
+  static const bool ldg_kernel = getenv("DQ_JK_LDG") != nullptr;      // A/B switch: the register-path (LDG) kernel
+  if (!ldg_kernel && smem3 <= 227 * 1024) {
+    ensure_dynamic_smem(k_jk_stream, smem3, true);
+    k_jk_stream<<<nchunks, 256, smem3, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+    return;
+  }
   ensure_dynamic_smem(k_jk_cols, smem2);
   k_jk_cols<<<nchunks, 256, smem2, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+}
+size_t jk_direct_smem_bytes(int kkmax, int N, int det) {
+  return ((size_t)2 * kkmax * kPairFields * 16 + 2 * 16 * 17 + 16 + (size_t)(det ? 24 : 16) * (N | 1)) * sizeof(double);
+}
+template <bool A, bool B, bool C, bool D>
+static void jk_direct_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
+                             const double* Dm, double* Jacc, double* Kacc, int kkmax, size_t smem) {
+  if (s.zero_skip) {
+    ensure_dynamic_smem(k_jk_direct<A, B, C, D, true>, smem > 100 * 1024 ? smem : 100 * 1024, true);
+    k_jk_direct<A, B, C, D, true><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, Dm, Jacc, Kacc, kkmax);
+  } else {
+    ensure_dynamic_smem(k_jk_direct<A, B, C, D, false>, smem > 100 * 1024 ? smem : 100 * 1024, true);
+    k_jk_direct<A, B, C, D, false><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, Dm, Jacc, Kacc, kkmax);
+  }
+  DQ_LAUNCHED();
+}
+void launch_jk_direct(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
+                      const double* D, double* Jacc, double* Kacc, int kkmax) {
+  if (nchunks <= 0) return;
+  const size_t smem = jk_direct_smem_bytes(kkmax, s.N, s.det);
+#define CALL(a, b, c, d) jk_direct_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, D, Jacc, Kacc, kkmax, smem)
+  DQ_CLASS_SWITCH(cls, CALL)
+#undef CALL
+}
+void launch_det_finalize(cudaStream_t st, long long n, const double* in, double* out, double beta) {
+  if (n <= 0) return;
+  k_det_finalize<<<cdiv(n, 256), 256, 0, st>>>(n, in, out, beta); DQ_LAUNCHED();
 }
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
                      double* g_xyz) {

@@ -28,6 +28,7 @@ inline void ensure_dynamic_smem(K kernel, size_t bytes, bool prefer_shared_carve
 }
 
 int upload_boys_constants();
+int* boys_fail_flag();          // device int of the current device: set when a Boys loop ran out of terms
 long long launch_count();
 void reset_launch_count();
 
@@ -54,6 +55,12 @@ void launch_scatter_packed(cudaStream_t st, const Tile* tiles, int nt, const Sys
                            double* packed);
 void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* store,
                       const double* D, double* Jacc, double* Kacc);
+// fixed-point accumulators (pairs of 64-bit limbs) -> doubles: out[i] = beta * out[i] + value
+void launch_det_finalize(cudaStream_t st, long long n, const double* in, double* out, double beta);
+// integral-direct J/K: the tiles of each chunk (same bra block pair) are evaluated and contracted with D inside one kernel
+size_t jk_direct_smem_bytes(int kkmax, int N, int det);
+void launch_jk_direct(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
+                      const double* D, double* Jacc, double* Kacc, int kkmax);
 void launch_pair_bwd(cudaStream_t st, const SystemDev& s, const double* padj, const double* pasum, double* g_alpha, double* g_coef,
                      double* g_xyz);
 void launch_gemm(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
@@ -79,7 +86,7 @@ void launch_boys(cudaStream_t st, int n, const double* t, double* F, double* dF)
 void launch_fp64_peak(cudaStream_t st, int blocks, int iters, double* out);
 
 // batched small-molecule path (dq_batch.cu)
-int upload_boys_constants_batch();
+int upload_boys_constants_batch(int* fail_flag);
 long long batch_launch_count();
 void reset_batch_launch_count();
 void launch_batch_prepare(cudaStream_t st, const BatchDev& b, const double* alpha_in, int log_alpha);
@@ -91,7 +98,8 @@ int launch_batch_scf(cudaStream_t st, const BatchDev& b, const double* S, const 
                      double* terms, int* nterms, double* Hbar, double* Sbar);
 void launch_batch_eri_grad(cudaStream_t st, int cls, const BatchDev& b, const int2* qlist, int nq, const double* terms, const int* nterms,
                            int max_scf, double* padj, double* pasum);
-void launch_batch_grad_finish(cudaStream_t st, const BatchDev& b, int log_alpha, const double* padj, const double* pasum, const double* Sbar,
-                              const double* Hbar, double* ga, double* gc, double* gx, double* graw);
+void launch_batch_grad_accumulate(cudaStream_t st, const BatchDev& b, const double* padj, const double* pasum, const double* Sbar,
+                                  const double* Hbar, double* ga, double* gc, double* gx);
+void launch_batch_grad_finish(cudaStream_t st, const BatchDev& b, int log_alpha, double* ga, const double* gc, double* graw);
 
 }  // namespace dq

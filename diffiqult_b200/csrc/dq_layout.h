@@ -49,6 +49,7 @@ struct SystemDev {
   int zero_skip;                 // 1 (default): primitive pairs whose Gaussian product underflowed to exactly 0 are left out of the loops
   unsigned long long* underflowed;   // counter: such primitive pairs (valid lanes), written by k_pairs
   const unsigned char* wmask;    // [N*N] gradient pass: is B_t[i,j] nonzero for some term t (every product in a weight has a B factor)
+  int det;                       // 1: accumulators are pairs of integer limbs (order-independent sums, dq_math.cuh det_add), 0: doubles + floating-point atomics
   unsigned long long* zero_weight;   // counter of contracted quartets the gradient pass skipped because their weight is exactly 0
 };
 
@@ -57,6 +58,7 @@ struct SystemDev {
 // their adjoints are molecule-fastest ([...][mol]) because the quartet kernels put neighbouring molecules in neighbouring lanes.
 struct BatchDev {
   int nmol, N, nprim, natoms, M, nrec, neri, kkmax, ne;
+  int det;                 // fixed-point (order-independent) gradient accumulators, see SystemDev::det
   const int* f_off;        // [N+1]
   const int* f_type;       // [N]  0 s, 1..3 p
   const int* Z;            // [natoms]

@@ -3,7 +3,11 @@
 The C library deals its ERI tiles round-robin to `world_size` ranks and asks the host for two kinds of exchange:
 one sum-allreduce of the partial J|K buffer per Fock build and one of the gradient buffer.  The callback built
 here wraps the device pointer it is handed as a torch tensor (no copy) and calls torch.distributed.all_reduce on
-the stream the library runs on.  With the gloo backend (CPU tests) the pointer is a host pointer.
+the stream the library hands it (the cudaStream_t of dq_options.stream), whatever torch's current stream is.  With the
+gloo backend (CPU tests) the pointer is a host pointer.
+
+Failure behaviour: a rank whose call fails before a collective leaves the other ranks blocked in it (NCCL semantics);
+treat any exception / non-zero status as fatal for the job (torchrun tears the other ranks down).
 """
 import ctypes as C
 
@@ -27,7 +31,7 @@ def make_allreduce(group=None, on_device=True):
     calls = {"n": 0, "doubles": 0}
     views = {}      # (pointer, count) -> tensor view: the library's pooled buffers keep their addresses from call to call
 
-    def _cb(ptr, count, user):
+    def _cb(ptr, count, stream, user):
         if on_device:
             t = views.get((ptr, count))
             if t is None:
@@ -37,7 +41,16 @@ def make_allreduce(group=None, on_device=True):
         else:
             buf = (C.c_double * count).from_address(ptr)
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if on_device:
+            # order the collective on the LIBRARY's stream: its kernels wrote the buffer there and will read it there
+            cur = torch.cuda.current_stream()
+            if int(stream or 0) == int(cur.cuda_stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            else:
+                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0))):
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         calls["n"] += 1
         calls["doubles"] += int(count)
 

@@ -4,6 +4,8 @@
  * would call instead of the Python functions cited beside each one.  Plain pointers and sizes only; all
  * pointers are HOST memory unless stated, FP64, row-major, int32 indices.  Every function returns a status
  * (0 = ok) and never exits the process (the reference's Boys failure paths call exit(): Tools.py:91,125,151).
+ * Negative statuses: -1 bad argument, -2 CUDA error, -3 no CUDA device (there is no CPU path), -4 size limit of the
+ * batched path, -5 a Boys-function loop did not converge (non-finite input; where the reference exits), -9 other.
  * No global mutable state besides the launch counter: callable from several host threads, one per GPU.
  *
  * Conventions shared with the reference:
@@ -37,9 +39,12 @@ typedef struct dq_system {
   int32_t log_alpha;
 } dq_system;
 
-/* in-place sum over ranks of `count` doubles at DEVICE pointer `dev`, ordered on the stream passed in
- * dq_options.stream.  Supplied by the host language (Python: torch.distributed.all_reduce over NCCL). */
-typedef void (*dq_allreduce_fn)(void* dev, int64_t count, void* user);
+/* in-place sum over ranks of `count` doubles at DEVICE pointer `dev`.  The collective must be enqueued ON `stream` (the
+ * cudaStream_t the library runs on, = dq_options.stream; NULL = the default stream): the buffer is written by kernels
+ * queued on that stream before the call and read by kernels queued on it afterwards.  Supplied by the host language
+ * (Python: torch.distributed.all_reduce over NCCL, diffiqult_b200/distributed.py).  If a rank fails before reaching a
+ * collective the other ranks block in it: abort the job on any non-zero status. */
+typedef void (*dq_allreduce_fn)(void* dev, int64_t count, void* stream, void* user);
 
 typedef struct dq_options {
   int32_t max_scf;         /* Energy.py:164   (Tasks defaults: 30 'Energy'/'Grad', 100 'Opt') */
@@ -51,13 +56,20 @@ typedef struct dq_options {
   dq_allreduce_fn allreduce;   /* required when world_size > 1: sums partial J|K and gradient buffers */
   void* allreduce_user;
   int32_t jk_mode;         /* Fock build (Energy.py:29-38): 0 auto, 1 stored ERI tiles (computed once, 8 B per contracted
-                            * quartet kept in HBM), 2 integral-direct (tiles recomputed batch by batch in every build) */
-  int64_t direct_batch_bytes;  /* integral-direct: size of the transient tile buffer (0: 1 GiB) */
+                            * quartet kept in HBM), 2 integral-direct (every build re-evaluates the tiles and contracts each one
+                            * with D inside the same kernel: nothing is stored) */
+  int64_t direct_batch_bytes;  /* unused since the fused integral-direct kernel (kept for ABI stability; was: transient buffer size) */
   double screen_threshold; /* 0 (default): every quartet is evaluated, as in the reference, which screens nothing.
                             * > 0 (opt-in): a tile is skipped when 2 pi^(5/2) max|K_ab| max|K_cd| over its two block
                             * pairs is below the threshold (an upper bound of its primitive prefactors) */
   const double* guess_C;   /* readguess (Energy.py:148-157): [nbasis*nbasis] AO x MO coefficients; the first Fock matrix is
                             * built from D = C_occ C_occ^T instead of the core Hamiltonian.  NULL: core guess */
+  int32_t accumulate;      /* how J, K, the pair adjoints and the gradient are summed over warps / CTAs: 0 or 1 (default) =
+                            * fixed point - every accumulator is a pair of 64-bit integer limbs (2^-24 and 2^-67 units), so the
+                            * sums do not depend on the order of the atomics and two calls on the same inputs return identical
+                            * bits (the reference's BFGS line search amplifies last-bit noise into different
+                            * iteration counts); 2 = double-precision floating-point atomics (results vary in the last bits
+                            * from run to run).  The environment variable DQ_ACCUM=fixed|float overrides. */
 } dq_options;
 
 typedef struct dq_stats {

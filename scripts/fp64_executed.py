@@ -1,13 +1,14 @@
 """profiles/fp64_executed.json from an ncu metrics pass over the ERI tile kernels and the J/K kernel of one bench step.
 
 On the GPU box (after the same command has exited 0 without ncu):
-    ncu --clock-control none --csv --log-file gpurun_out/fp64.csv -k regex:'k_eri_(grad_)?(tiles|tiles_compact|chunks|sparse)|k_jk_cols' -c 39 --metrics \
+    ncu --clock-control none --csv --log-file gpurun_out/fp64.csv -k regex:'k_eri_(grad_)?(tiles|tiles_compact|chunks|sparse)|k_jk_(cols|stream)' -c 40 --metrics \
       smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,\
       smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,\
       smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,\
       dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,launch__registers_per_thread \
-      python bench.py --steps 1 --warmup 1 --no-cpu-baseline
-Here:  python scripts/fp64_executed.py gpurun_out/fp64.csv <primitive quartets evaluated per pass (dq_stats.n_prim_quartets)>
+      python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras [--spacing 24]
+Here:  python scripts/fp64_executed.py gpurun_out/fp64.csv <primitive quartets evaluated per pass (dq_stats.n_prim_quartets)> \
+           [profiles/fp64_executed_dense.json] [profiles/r2_fp64_executed_dense.csv]
 """
 import collections
 import csv
@@ -16,6 +17,8 @@ import shutil
 import sys
 
 src, npq = sys.argv[1], float(sys.argv[2])
+out_json = sys.argv[3] if len(sys.argv) > 3 else "profiles/fp64_executed.json"
+out_csv = sys.argv[4] if len(sys.argv) > 4 else "profiles/r1_fp64_executed.csv"
 rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"')) if len(r) > 14 and r[0] != "ID"]
 per = collections.OrderedDict()
 for r in rows:
@@ -34,7 +37,7 @@ for (_, name), m in per.items():
     a["ns"] += ns
     a["pipe_ns"] += ns * m.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", 0.0) / 100.0
     a["dram"] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
-out = {"source": "profiles/r1_fp64_executed.csv (ncu metrics pass of `bench.py --steps 1 --warmup 1`, first step)",
+out = {"source": "%s (ncu metrics pass of one bench.py step)" % out_csv,
        "primitive_quartets_evaluated_per_pass": npq}
 for f, a in fam.items():
     e = {"launches": a["launches"], "ms_under_ncu": a["ns"] * 1e-6, "executed_flop": a["flop"],
@@ -47,6 +50,6 @@ for f, a in fam.items():
     else:
         e["dram_bytes_per_launch"] = a["dram"] / a["launches"]
     out[f] = e
-json.dump(out, open("profiles/fp64_executed.json", "w"), indent=1)
-shutil.copy(src, "profiles/r1_fp64_executed.csv")
+json.dump(out, open(out_json, "w"), indent=1)
+shutil.copy(src, out_csv)
 print(json.dumps(out, indent=1))

@@ -37,8 +37,8 @@ def main():
     cb = distributed.make_allreduce()
     stream = distributed.current_stream_handle()
     cases = {"ch2o": System_mol(synthetic.CH2O, basis_set_3G_STO, 16, "ch2o"),
-             "w2": System_mol(synthetic.water_cluster(2), basis_set_3G_STO, 20, "w2"),
-             "w%d" % args.waters: System_mol(synthetic.water_cluster(args.waters), basis_set_3G_STO, 10 * args.waters, "wn")}
+             "w2": System_mol(synthetic.water_cluster(2, spacing=24.0), basis_set_3G_STO, 20, "w2"),
+             "w%d" % args.waters: System_mol(synthetic.water_cluster(args.waters, spacing=24.0), basis_set_3G_STO, 10 * args.waters, "wn")}
     report, ok = {}, True
     for name, s in cases.items():
         a = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)

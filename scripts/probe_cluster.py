@@ -10,7 +10,7 @@ tf = C.c_double(0)
 _capi.check(_capi.lib().dq_fp64_peak(C.c_int32(0), C.byref(tf)))
 print("fp64 FMA peak TFLOP/s", tf.value, flush=True)
 for n in [int(x) for x in sys.argv[1].split(",")]:
-    mol = synthetic.water_cluster(n)
+    mol = synthetic.water_cluster(n, spacing=24.0)
     s = System_mol(mol, basis_set_3G_STO, 10 * n, "w%d" % n)
     for grad in (False, True):
         t0 = time.time()

@@ -140,11 +140,11 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     cb = distributed.make_allreduce(on_device=False)
     buf = np.arange(10, dtype=np.float64) * (rank + 1)
-    cb(buf.ctypes.data, 10, None)                      # what the C library does with its partial J|K buffer
+    cb(buf.ctypes.data, 10, None, None)                    # what the C library does with its partial J|K buffer
     a = _arrays("ch2o")
     mine = capi.plan(a, world, rank)
     cnt = np.array([mine["tiles"], mine["quartets"], mine["prim_quartets"]], dtype=np.float64)
-    cb(cnt.ctypes.data, 3, None)
+    cb(cnt.ctypes.data, 3, None, None)
     q.put((rank, buf.tolist(), cnt.tolist(), cb.calls["n"]))
     dist.destroy_process_group()
 
