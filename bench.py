@@ -314,6 +314,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    if args.profile_range:            # ncu --profile-from-start off: only the timed steps are captured (not the guess SCFs)
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     stats = []
     for _ in range(args.steps):
@@ -321,6 +323,8 @@ def run_ours(args):
         stats.append(r["stats"])
     barrier()
     wall = time.perf_counter() - t0
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     dev_ms = float(np.sum([st["ms_total"] - st["ms_setup"] for st in stats]))
@@ -486,6 +490,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys measured after the timed region "
                     "(integral-direct step, the 24-bohr core-guess workload, config 5)")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     ap.add_argument("--core-guess", action="store_true", help="start from the core Hamiltonian even on a dense grid (does not converge)")
     ap.add_argument("--ref-waters", type=int, default=REF_SAMPLE_WATERS, help="--impl reference: monomers in the bounded CPU sample")
     ap.add_argument("--jk-mode", default="auto", choices=["auto", "stored", "direct"])

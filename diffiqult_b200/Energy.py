@@ -54,9 +54,10 @@ def rhf(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30,
 
 def rhf_grad(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_scf=30, log=True, device=0, stream=None,
              world_size=1, rank=0, allreduce=None, jk_mode="auto", direct_batch_bytes=0, screen_threshold=0.0, guess_C=None,
-             accumulate="fixed"):
+             accumulate="fixed", atoms_grad=False):
     """Energy and its gradient w.r.t. (alpha as passed, raw coefficients, Gaussian centres) in one fused pass:
-    dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats).  accumulate="fixed" (default): order-independent
+    dict(E, status, niter, grad=[g_alpha, g_coef, g_xyz], stats).  atoms_grad=True adds grad_atoms[natoms*3], the gradient
+    w.r.t. the nuclear coordinates with the Gaussians held fixed (the reference's branch Energy.py:125-130).  accumulate="fixed" (default): order-independent
     fixed-point sums, two calls on the same inputs return identical bits; "float": floating-point atomics."""
     _check_max_scf(max_scf)
     a = _sys(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, log)
@@ -66,9 +67,13 @@ def rhf_grad(alpha_old, coef2, xyz, l, charges, xyz_atom, contr_list, ne, max_sc
     opt = _capi.options(max_scf=max_scf, device=device, stream=stream, world_size=world_size, rank=rank, allreduce=allreduce,
                         jk_mode=jk_mode, direct_batch_bytes=direct_batch_bytes, screen_threshold=screen_threshold, guess_C=guess,
                         accumulate=accumulate)
-    st = _capi.check(_capi.lib().dq_rhf_grad(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), ga.ctypes, gc.ctypes,
-                                             gx.ctypes), allow=(0, 1))
-    return dict(E=E.value, status=st, niter=nit.value, grad=[ga, gc, gx], stats=_capi.stats())
+    gn = np.zeros(3 * a.natoms) if atoms_grad else None
+    st = _capi.check(_capi.lib().dq_rhf_grad_ex(C.byref(a.struct), C.byref(opt), C.byref(E), C.byref(nit), ga.ctypes, gc.ctypes,
+                                                gx.ctypes, gn.ctypes if atoms_grad else None), allow=(0, 1))
+    out = dict(E=E.value, status=st, niter=nit.value, grad=[ga, gc, gx], stats=_capi.stats())
+    if atoms_grad:
+        out["grad_atoms"] = gn
+    return out
 
 
 def rhfenergy(alpha_old, coef2, xyz, l, charges, xyz_atom, natoms, nbasis, contr_list, ne, max_scf, max_d, log, eigen,

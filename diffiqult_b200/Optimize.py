@@ -20,8 +20,12 @@ import warnings
 
 import numpy as np
 from scipy.optimize import OptimizeResult
-from scipy.optimize._dcsrch import DCSRCH
-from scipy.optimize._linesearch import line_search_wolfe2, LineSearchWarning
+try:    # private SciPy modules (>= 1.12 ships the Python DCSRCH port; pinned in requirements.txt): fail with a clear message
+    from scipy.optimize._dcsrch import DCSRCH
+    from scipy.optimize._linesearch import line_search_wolfe2, LineSearchWarning
+except ImportError as _e:      # pragma: no cover
+    raise ImportError("diffiqult_b200.Optimize needs scipy.optimize._dcsrch.DCSRCH and scipy.optimize._linesearch "
+                      "(SciPy >= 1.12, see requirements.txt); found SciPy without them: %s" % _e)
 
 SCF_FAILED = 99999
 

@@ -27,15 +27,15 @@ args_dict = {0: 'Exponents', 1: 'Contraction coefficients', 2: 'Gaussian centers
 class _GradCache(object):
     """One fused device call serves all argument groups evaluated at the same point."""
 
-    def __init__(self):
-        self.key, self.val = None, None
+    def __init__(self, atoms_grad=False):
+        self.key, self.val, self.atoms_grad = None, None, atoms_grad
 
     def get(self, args, device):
-        key = tuple(np.asarray(args[k], dtype=np.float64).tobytes() for k in (0, 1, 2)) + (int(args[10]), bool(args[12]), args[15])
+        key = tuple(np.asarray(args[k], dtype=np.float64).tobytes() for k in (0, 1, 2, 5)) + (int(args[10]), bool(args[12]), args[15])
         if key != self.key:
             guess = np.load(args[15]) if args[15] is not None else None     # readguess slot (Energy.py:148-149)
             r = _energy.rhf_grad(args[0], args[1], args[2], args[3], args[4], args[5], args[8], args[9],
-                                 max_scf=args[10], log=args[12], device=device, guess_C=guess)
+                                 max_scf=args[10], log=args[12], device=device, guess_C=guess, atoms_grad=self.atoms_grad)
             self.key, self.val = key, r
         return self.val
 
@@ -43,17 +43,20 @@ class _GradCache(object):
 def function_grads_algopy(function, argnum, device=0):
     """Task.py:25-41: list of callables, one per entry of argnum, each returning dE/d(args[n]) flattened.
     (The name is the reference's; no algopy is involved: the derivative is the fused adjoint pass.)"""
-    cache = _GradCache()
+    cache = _GradCache(atoms_grad=5 in argnum)
 
     def builder(narg):
-        if narg not in (0, 1, 2):
-            raise NotImplementedError("gradients exist for argnum 0 (widths), 1 (contraction coefficients), 2 (centers)")
+        # slot 5 of the argument list is xyz_atom: the reference's nuclear-coordinate branch (Energy.py:125-130), which its
+        # own Tasks never reaches.  (Its args_dict labels slot 4 'Geometry centers', but slot 4 holds the nuclear CHARGES.)
+        if narg not in (0, 1, 2, 5):
+            raise NotImplementedError("gradients exist for argnum 0 (widths), 1 (contraction coefficients), 2 (Gaussian centers) "
+                                      "and 5 (nuclear coordinates, Energy.py:125-130)")
 
         def grad(*args, **kwargs):
             r = cache.get(args, device)
             if r["status"] != 0:
                 raise FloatingPointError("SCF did not converge: no gradient (the reference fails in extract_jacobian)")
-            return np.array(r["grad"][narg])
+            return np.array(r["grad_atoms"] if narg == 5 else r["grad"][narg])
         return grad
     return [builder(i) for i in argnum]
 
@@ -61,6 +64,33 @@ def function_grads_algopy(function, argnum, device=0):
 def grad_evaluator_algopy(function, args, argnum, device=0, **kwargs):
     """Task.py:44-51."""
     return [g(*args, **kwargs) for g in function_grads_algopy(function, argnum, device=device)]
+
+
+def function_hessian_algopy(function, argnum, device=0, step=1e-4):
+    """Task.py:55-70: list of callables, one per entry of argnum, each returning the Hessian d2E/d(args[n])^2 as a
+    (P, P) array.  The reference pushes a second-order UTPM through rhfenergy (UTPM.init_hessian / extract_hessian; it
+    is never called from Tasks).  Here: central differences of the fused ADJOINT gradient, 2P device calls, symmetrised;
+    error O(step^2) + rounding/step, ~1e-7 with the default step.  Note the reference's signature: algo_jaco(args), the
+    argument LIST, not *args (Task.py:60)."""
+    def builder(narg):
+        grad = function_grads_algopy(function, [narg], device=device)[0]
+
+        def hess(args, **kwargs):
+            x0 = np.array(args[narg], dtype=np.float64)
+            flat = x0.ravel()
+            H = np.zeros((flat.size, flat.size))
+            for i in range(flat.size):
+                g = []
+                for sgn in (+1.0, -1.0):
+                    x = flat.copy()
+                    x[i] += sgn * step
+                    a2 = list(args)
+                    a2[narg] = x.reshape(x0.shape)
+                    g.append(np.ravel(grad(*a2, **kwargs)))
+                H[i] = (g[0] - g[1]) / (2.0 * step)
+            return 0.5 * (H + H.T)
+        return hess
+    return [builder(i) for i in argnum]
 
 
 class Tasks(object):
@@ -216,7 +246,7 @@ class Tasks(object):
 
     def optimization(self, max_scf=100, log=True, scf=True, name='Output', readguess=None, output=False, argnum=[0], **kwargs):
         name = self.name + '-task-' + str(self.ntask)
-        kwargs = {k: v for k, v in kwargs.items() if k in ('maxiter', 'reference_linesearch')}
+        kwargs = {k: v for k, v in kwargs.items() if k in ('maxiter', 'reference_linesearch', 'return_all')}
         self._optimization(max_scf, log, scf, readguess, argnum, taskname=name, **kwargs)
 
     # ------------------------------------------------------------------ dispatch (Task.py:435-473)

@@ -41,7 +41,7 @@ class dq_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["dq_plan", "dq_normalization", "dq_one_electron", "dq_eri_packed", "dq_fock", "dq_rhf", "dq_rhf_grad", "dq_rhf_grad_batch", "dq_eigh",
+EXPORTS = ["dq_plan", "dq_normalization", "dq_one_electron", "dq_eri_packed", "dq_fock", "dq_rhf", "dq_rhf_grad", "dq_rhf_grad_ex", "dq_rhf_grad_batch", "dq_eigh",
            "dq_boys", "dq_fp64_peak", "dq_get_stats", "dq_last_error", "dq_device_count", "dq_release_cache"]
 
 _lib = None

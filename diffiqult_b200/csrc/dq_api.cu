@@ -263,9 +263,34 @@ static void prepare(Prepared& P, const dq_system* s, const dq_options* opt, bool
   // sort functions by (type, contraction length); stable so that equal keys keep the caller's order
   P.f_orig.resize(N);
   for (int i = 0; i < N; ++i) P.f_orig[i] = i;
+  // Inside a (type, contraction length) group the order decides which four functions share a block, i.e. which quartets
+  // share a warp.  All lanes of a warp walk the same primitive indices, so a warp's Boys arguments t = rho |PQ|^2 are alike -
+  // and its lanes take the same branch of the Boys function with similar trip counts - when the functions of a block have
+  // like exponents and nearby centres: sort by the largest exponent (quarter-octave buckets), then along a Morton curve.
+  // The tile plan depends on the group sizes only, so it stays cached while parameters move.  DQ_SORT=0: caller's order.
+  static const int sort_mode = getenv("DQ_SORT") ? atoi(getenv("DQ_SORT")) : 1;
+  std::vector<long long> key2(N, 0);
+  if (sort_mode >= 1) {
+    double lo[3] = {1e300, 1e300, 1e300};
+    for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) lo[c] = std::min(lo[c], s->xyz[3 * i + c]);
+    for (int i = 0; i < N; ++i) {
+      double amax = 0.0;
+      for (int p = 0; p < s->contr[i]; ++p) {
+        const double a = s->log_alpha ? exp(s->alpha[off[i] + p]) : s->alpha[off[i] + p];
+        amax = std::max(amax, a);
+      }
+      long long bucket = amax > 0.0 ? (long long)floor(4.0 * log2(amax)) + 4096 : 0;
+      unsigned long long morton = 0;
+      unsigned g[3];
+      for (int c = 0; c < 3; ++c) { const double q = (s->xyz[3 * i + c] - lo[c]) / 2.0; g[c] = q > 0 ? (q < 1023 ? (unsigned)q : 1023u) : 0u; }   // 2-bohr cells
+      for (int b = 9; b >= 0; --b) for (int c = 2; c >= 0; --c) morton = (morton << 1) | ((g[c] >> b) & 1u);
+      key2[i] = sort_mode == 1 ? (bucket << 32) | (long long)morton : (long long)morton;
+    }
+  }
   std::stable_sort(P.f_orig.begin(), P.f_orig.end(), [&](int a, int b) {
     if (s->ltype[a] != s->ltype[b]) return s->ltype[a] < s->ltype[b];
-    return s->contr[a] < s->contr[b];
+    if (s->contr[a] != s->contr[b]) return s->contr[a] < s->contr[b];
+    return key2[a] < key2[b];
   });
   std::vector<int> foff(N + 1, 0), ftype(N), fblock(N);
   std::vector<double> xyz(3 * N), alpha(s->nprim), craw(s->nprim);
@@ -578,7 +603,7 @@ static double nuclear_repulsion(const dq_system* s) {   // Energy.py:21-27 (O(na
 struct ScfOut { double E = 0; int niter = 0; bool converged = false; std::vector<double> esteps, C, eps; };
 
 static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool want_grad, double* g_alpha, double* g_coef,
-                    double* g_xyz) {
+                    double* g_xyz, double* g_atoms = nullptr) {
   memset(&t_stats, 0, sizeof t_stats);
   reset_launch_count();
   Prepared P;
@@ -857,6 +882,15 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     if (det) CU(cudaMemsetAsync(gacc, 0, sizeof(double) * 2 * glen, st));
     launch_one_electron_grad(st, P.sd, P.kmax, Sbar, Hbar, aa, ac, ax);
     if (det) launch_det_finalize(st, glen, gacc, gbuf, 1.0);
+    // nuclear coordinates (Energy.py:125-130: only V and E_nuc depend on them; the Gaussians do not follow the nuclei)
+    double* natom_buf = nullptr;
+    if (g_atoms && s->natoms > 0) {
+      const long long na = 3LL * s->natoms;
+      double* nacc = ws.alloc<double>(na * lm, true);
+      launch_nuclear_grad(st, P.sd, P.kmax, Hbar, nacc);
+      natom_buf = nacc;
+      if (det) { natom_buf = ws.alloc<double>(na); launch_det_finalize(st, na, nacc, natom_buf, 0.0); }
+    }
     double* graw = ws.alloc<double>(P.nprim);
     launch_normalize_bwd(st, n, P.d_foff, P.d_ftype, P.d_alpha, P.d_craw, gc, ga, graw);
     if (P.log_alpha) launch_mul(st, P.nprim, ga, P.d_alpha, ga);                   // d/d ln(alpha) = alpha d/d alpha
@@ -866,7 +900,18 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
     CU(cudaMemcpyAsync(ha.data(), ga, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hc.data(), graw, P.nprim * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hx.data(), gx, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (natom_buf) CU(cudaMemcpyAsync(g_atoms, natom_buf, 3 * s->natoms * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (natom_buf) {      // + dE_nuc/dR_i = sum_j Z_i Z_j (R_j - R_i) / |R_i - R_j|^3          (Energy.py:21-27)
+      for (int i = 0; i < s->natoms; ++i)
+        for (int j = 0; j < s->natoms; ++j) {
+          if (j == i) continue;
+          double d[3], r2 = 0;
+          for (int c = 0; c < 3; ++c) { d[c] = s->atoms[3 * j + c] - s->atoms[3 * i + c]; r2 += d[c] * d[c]; }
+          const double f = s->charges[i] * s->charges[j] / (r2 * sqrt(r2));
+          for (int c = 0; c < 3; ++c) g_atoms[3 * i + c] += f * d[c];
+        }
+    }
     for (int p = 0; p < P.nprim; ++p) { if (g_alpha) g_alpha[P.p_orig[p]] = ha[p]; if (g_coef) g_coef[P.p_orig[p]] = hc[p]; }
     if (g_xyz) for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) g_xyz[3 * P.f_orig[i] + c] = hx[3 * i + c];
     t_stats.ms_grad_other = t_g.stop() - t_stats.ms_eri_grad;
@@ -1187,6 +1232,17 @@ int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t*
   try {
     ScfOut o;
     run_rhf(sys, opt, o, true, g_alpha, g_coef, g_xyz);
+    if (E) *E = o.E;
+    if (niter) *niter = o.niter;
+    return o.converged ? 0 : 1;
+  } catch (const Fail& f) { return f.code; } catch (const std::exception& e) { t_err = e.what(); return -9; }
+}
+
+int dq_rhf_grad_ex(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha, double* g_coef,
+                   double* g_xyz, double* g_atoms) {
+  try {
+    ScfOut o;
+    run_rhf(sys, opt, o, true, g_alpha, g_coef, g_xyz, g_atoms);
     if (E) *E = o.E;
     if (niter) *niter = o.niter;
     return o.converged ? 0 : 1;

