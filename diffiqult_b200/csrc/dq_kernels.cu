@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
 }
 
 // ---------------------------------------------------------------------------------------------
-// ERI tiles with WARP-BATCHED Boys evaluation (the default).  ncu on the dense (H2O)_32 cluster: 79 % of the primitive
+// ERI tiles with WARP-BATCHED Boys evaluation (opt-in: DQ_ERI_KERNEL=batched; measured SLOWER than the plain kernel, see
+// eri_launch - kept for A/B runs).  ncu on the dense (H2O)_32 cluster: 79 % of the primitive
 // quartets have t >= 50 (closed form), but 46 % of a warp's primitive-quartet steps contain at least one lane below it, and
 // then the whole warp walks exp(-t) and the series / continued-fraction loops of every order with 14.7 of its 32 lanes
 // active (2.9 in the series loops): 45 % of all warp instructions at < 50 % lane use.  The slow evaluations are therefore
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(256) k_eri_tiles_b(const Tile* __restrict__ ti
         const double d[3] = {bra.P[0] - krec[c.kt], bra.P[1] - krec[16 + c.kt], bra.P[2] - krec[32 + c.kt]};
         const bool on = bon && !(ZS && krec[80 + c.kt] == 0.0);
         const double t = quartet_t(bra.g, krec[48 + c.kt], d);
-        const bool slow = on && t < kBoysAsymptotic;
+        const bool slow = on && t < boys_asymptotic_from<L>();
         const unsigned bal = __ballot_sync(0xffffffffu, slow);
         if (slow) {
           const int tk = ntask + __popc(bal & lt);
@@ -778,20 +779,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) k_jk_stream(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
+// PRIV: every warp accumulates its exchange contributions in a PRIVATE pair of K row strips (plain shared-memory
+// read-modify-writes in program order: no atomics, no fixed-point conversion in the inner loop, and - the order being
+// fixed - bit-reproducible as it stands); the eight strips are summed in warp order at the end of the chunk and flushed
+// once.  Needs 8 x 8 x N doubles of shared memory on top of the ring (N = 224: 198 KB, one CTA per SM).  Opt-in
+// (DQ_JK_PRIVATE=1): with the shared strips the kernel is bound by instruction issue, not by HBM (356 warp instructions per
+// 2 KB tile, a third of them the compare-and-swap loops of 8 shared-memory atomics per lane), but eight warps per SM do not
+// hide the latency of a stage: measured slower (0.96 against 0.74 ms per build).
+template <bool PRIV>
+__global__ void __launch_bounds__(256, PRIV ? 1 : 2) k_jk_stream(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s,
                                                       const double* __restrict__ store, const double* __restrict__ D,
                                                       double* __restrict__ Jacc, double* __restrict__ Kacc) {
   extern __shared__ __align__(128) double sm[];
   const int n = s.N, tid = threadIdx.x;
   const int ns = n | 1;
   const int det = s.det;
-  const int nk = (det ? 16 : 8) * ns;
+  const int nk = PRIV ? 64 * ns : (det ? 16 : 8) * ns;     // PRIV: [8 warps][8][ns] doubles
   double* ring = sm;                                        // [8 warps][kJkSlots][2 tiles][256]  (first: 128-byte aligned)
   unsigned long long* bars = (unsigned long long*)(ring + 8 * kJkSlots * 2 * kTile);      // [8][kJkSlots]
   JkDesc* desc = (JkDesc*)(bars + 8 * kJkSlots);            // [256]
   double* sdij = (double*)(desc + 256);                     // [16]
   double* dstrip = sdij + 16;                               // [8][ns]
-  double* kstrip = dstrip + 8 * ns;                         // [8][ns] (x 2 limbs)
+  double* kstrip = dstrip + 8 * ns;                         // [8][ns] (x 2 limbs), PRIV: [8 warps][8][ns]
   const int2 ch = chunks[blockIdx.x];
   const int bp1 = tiles[ch.x].bp1;
   const BlockPair b1 = s.bp[bp1];
@@ -884,7 +893,26 @@ __global__ void __launch_bounds__(256, 2) k_jk_stream(const Tile* __restrict__ t
     const double kil = reduce_scatter4(b[0], b[1], b[2], b[3], k >> 1, k & 1, 8, 4);
     const double kjk = reduce_scatter4(c[0], c[1], c[2], c[3], l >> 1, l & 1, 2, 1);
     const double kjl = reduce_scatter4(e[0], e[1], e[2], e[3], k >> 1, k & 1, 8, 4);
-    if (act) {
+    if (PRIV) {
+      // the two tiles of the stage (half-warps) hit the same strip elements when they share the K (or the L) block:
+      // then the upper half hands its weighted values to the lower half; otherwise the 32 targets are distinct
+      double* kp = kstrip + (size_t)warp * 8 * ns;
+      const int osK = __shfl_xor_sync(0xffffffffu, d.sK, 16), osL = __shfl_xor_sync(0xffffffffu, d.sL, 16);
+      const bool oact = __shfl_xor_sync(0xffffffffu, (int)act, 16) != 0;
+      const bool sameK = act && oact && osK == d.sK, sameL = act && oact && osL == d.sL;
+      double x0 = (act && k < d.nK) ? w * kik : 0.0, x1 = (act && k < d.nK) ? w * kjk : 0.0;
+      double y0 = (act && l < d.nL) ? w * kil : 0.0, y1 = (act && l < d.nL) ? w * kjl : 0.0;
+      const double ox0 = __shfl_xor_sync(0xffffffffu, x0, 16), ox1 = __shfl_xor_sync(0xffffffffu, x1, 16);
+      const double oy0 = __shfl_xor_sync(0xffffffffu, y0, 16), oy1 = __shfl_xor_sync(0xffffffffu, y1, 16);
+      if (sameK) { x0 = h ? 0.0 : x0 + ox0; x1 = h ? 0.0 : x1 + ox1; }
+      if (sameL) { y0 = h ? 0.0 : y0 + oy0; y1 = h ? 0.0 : y1 + oy1; }
+      if (x0 != 0.0) kp[l * ns + ck] += x0;
+      if (x1 != 0.0) kp[(4 + l) * ns + ck] += x1;
+      __syncwarp();                     // a diagonal ket (K == L) makes the next two adds revisit these elements
+      if (y0 != 0.0) kp[k * ns + cl] += y0;
+      if (y1 != 0.0) kp[(4 + k) * ns + cl] += y1;
+      __syncwarp();
+    } else if (act) {
       if (k < d.nK) {
         if (kik != 0.0) acc_add(kstrip, l * ns + ck, w * kik, det);
         if (kjk != 0.0) acc_add(kstrip, (4 + l) * ns + ck, w * kjk, det);
@@ -909,7 +937,12 @@ __global__ void __launch_bounds__(256, 2) k_jk_stream(const Tile* __restrict__ t
   for (int x = tid; x < 8 * ns; x += 256) {
     const int row = x / ns, col = x - row * ns, r = row & 3;
     const long long g = (long long)((row >= 4 ? b1.sJ : b1.sI) + r) * n + col;
-    if (det) {
+    if (PRIV) {
+      double val = 0.0;
+#pragma unroll
+      for (int wp = 0; wp < 8; ++wp) val += kstrip[(size_t)wp * 8 * ns + x];      // fixed order
+      if (val != 0.0 && col < n && r < (row >= 4 ? b1.nJ : b1.nI)) acc_add(Kacc, g, val, det);
+    } else if (det) {
       const unsigned long long* sp = (const unsigned long long*)kstrip + 2 * x;
       unsigned long long* gp = (unsigned long long*)Kacc + 2 * g;
       if (sp[0]) atomicAdd(gp, sp[0]);
@@ -2200,7 +2233,11 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
-  static const bool plain = getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'p';     // A/B: "plain" = unbatched Boys
+  // default: the plain kernel (Boys function evaluated in place).  DQ_ERI_KERNEL=batched selects the warp-batched variant
+  // for A/B runs: measured on the dense (H2O)_32 cluster it raises the lanes per instruction from 17.7 to 23.5 but executes
+  // 211 instead of 132 thread instructions per primitive quartet (arguments computed twice, task lists, values through
+  // shared memory): 305 ms against 282 ms for the pass.
+  static const bool plain = !(getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'b');
   constexpr int L = (int)A + (int)B + (int)C + (int)D;
   const size_t smem_b = smem + (size_t)8 * kBoysCap * (L + 2) * sizeof(double);
   if (!plain && smem_b <= 200 * 1024) {
@@ -2314,9 +2351,19 @@ void launch_jk_chunks(cudaStream_t st, const Tile* tiles, const int2* chunks, in
   const size_t smem2 = ((size_t)(s.det ? 24 : 16) * (s.N | 1) + 16) * sizeof(double) + 256 * 16;
   const size_t smem3 = smem2 + (size_t)8 * kJkSlots * 2 * kTile * sizeof(double) + 8 * kJkSlots * sizeof(unsigned long long);
   static const bool ldg_kernel = getenv("DQ_JK_LDG") != nullptr;      // A/B switch: the register-path (LDG) kernel
+  // A/B switch DQ_JK_PRIVATE=1: private K strips per warp (no atomics in the loop, but 198 KB of shared memory = one CTA
+  // of 8 warps per SM: measured 0.96 ms per build on the dense (H2O)_32 cluster against 0.74 ms for the shared strips)
+  static const bool private_strips = getenv("DQ_JK_PRIVATE") != nullptr;
+  const size_t ring = (size_t)8 * kJkSlots * 2 * kTile * sizeof(double) + 8 * kJkSlots * sizeof(unsigned long long);
+  const size_t smemp = ((size_t)72 * (s.N | 1) + 16) * sizeof(double) + 256 * 16 + ring;     // private strips per warp
+  if (!ldg_kernel && private_strips && smemp <= 227 * 1024) {
+    ensure_dynamic_smem(k_jk_stream<true>, smemp, true);
+    k_jk_stream<true><<<nchunks, 256, smemp, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+    return;
+  }
   if (!ldg_kernel && smem3 <= 227 * 1024) {
-    ensure_dynamic_smem(k_jk_stream, smem3, true);
-    k_jk_stream<<<nchunks, 256, smem3, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
+    ensure_dynamic_smem(k_jk_stream<false>, smem3, true);
+    k_jk_stream<false><<<nchunks, 256, smem3, st>>>(tiles, chunks, s, store, D, Jacc, Kacc); DQ_LAUNCHED();
     return;
   }
   ensure_dynamic_smem(k_jk_cols, smem2);
