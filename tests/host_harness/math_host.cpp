@@ -18,11 +18,25 @@ static double runv(const PairPrim& bra, const PairPrim& ket, const int* l) {
   return prim_quartet_axes<LA, LB, LC, LD, false>(bra, ket, l[0] - 1, l[1] - 1, l[2] - 1, l[3] - 1, g_bc, 0.0, nullptr, nullptr, nullptr);
 }
 
+// the same for a kernel of angular class L (orders 0..L; the regime boundaries of boys_ref depend on L): F,dF: [n][5]
+template <int L> static void boys_class(int n, const double* t, double* F, double* dF) {
+  for (int i = 0; i < n; ++i) boys_ref<L, true>(t[i], g_bc, F + 5 * i, dF + 5 * i);
+}
 extern "C" {
 
 void hh_boys(int n, const double* t, double* F, double* dF) {  // F,dF: [n][5]
   init();
   for (int i = 0; i < n; ++i) boys_ref<4, true>(t[i], g_bc, F + 5 * i, dF + 5 * i);
+}
+void hh_boys_class(int L, int n, const double* t, double* F, double* dF) {
+  init();
+  switch (L) {
+    case 0: boys_class<0>(n, t, F, dF); break;
+    case 1: boys_class<1>(n, t, F, dF); break;
+    case 2: boys_class<2>(n, t, F, dF); break;
+    case 3: boys_class<3>(n, t, F, dF); break;
+    default: boys_class<4>(n, t, F, dF); break;
+  }
 }
 void hh_boys_value(int n, const double* t, double* F) {
   init(); double d[5];

@@ -51,6 +51,22 @@ def test_boys_value_and_derivative_dense_grid(hh):
         assert (np.abs(dF[:, m] - dFo) < bound).all(), m
 
 
+@pytest.mark.parametrize("L", [0, 1, 2, 3, 4])
+def test_boys_regimes_of_every_angular_class_match_the_reference_loops(hh, L):
+    """boys_ref<L> switches, per angular class, from the reference's loops to the loop-free mid-range form (t >= 13 / 16 /
+    18 / 20 / 20) and to the closed form (t >= 36 / 39.5 / 42.5 / 45 / 47.5).  Dense scan across both boundaries against
+    the oracle (= the reference's series / continued fraction with its stopping rules, Tools.py:78-151): relative to
+    F_m, because the high orders are small there."""
+    t = np.concatenate([np.arange(6.0, 60.0, 0.002), [13.0, 16.0, 18.0, 20.0, 36.0, 39.5, 42.5, 45.0, 47.5, 50.0]])
+    F = np.zeros((t.size, 5))
+    dF = np.zeros((t.size, 5))
+    hh.hh_boys_class(C.c_int(L), C.c_int(t.size), t.ctypes, F.ctypes, dF.ctypes)
+    for m in range(L + 1):
+        Fo, dFo = orc.boys(t, m)
+        assert (np.abs(F[:, m] - Fo) / np.abs(Fo)).max() < 4e-15, (L, m)
+        assert (np.abs(dF[:, m] - dFo) / np.abs(dFo)).max() < 3e-12, (L, m)
+
+
 def _rand_prims(rng, spread):
     ex = np.exp(rng.uniform(np.log(0.15), np.log(40.0), 4))
     co = rng.uniform(0.2, 1.5, 4) * rng.choice([-1.0, 1.0], 4)
