@@ -97,7 +97,7 @@ def test_fock_build_vs_oracle(name):
     assert np.abs(F - Fo).max() < 1e-10 * max(1.0, np.abs(Fo).max())
 
 
-@pytest.mark.parametrize("n,batch", [(1, 3), (2, 4), (3, 2), (7, 5), (16, 2), (33, 2), (48, 2), (49, 1), (64, 3), (101, 2), (224, 1), (236, 1)])
+@pytest.mark.parametrize("n,batch", [(1, 3), (2, 4), (3, 2), (7, 5), (16, 2), (33, 2), (48, 2), (49, 1), (64, 3), (101, 2), (224, 1), (236, 1), (260, 1)])
 def test_eigensolver(n, batch):
     rng = np.random.default_rng(n)
     A = rng.normal(size=(batch, n, n)); A = A + A.transpose(0, 2, 1)
