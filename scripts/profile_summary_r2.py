@@ -126,6 +126,7 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("loops unrolled in value kernels, rolled in gradient kernels (final)", "230-237", "565", "0.74", "827-835"),
             ("row-compacted loop regime in the value kernel (reverted)", "234-249", "566", "0.74", "832-849"),
             ("private K strips per warp (`DQ_JK_PRIVATE=1`)", "-", "-", "0.96", "-"),
+            ("K-run J/K kernel (no strip atomics, one CTA barrier per run; reverted)", "-", "-", "0.94", "-"),
             ("`DQ_JK_LDG=1` (register-path loads instead of the TMA ring)", "-", "-", "0.79", "-"),
             ("`DQ_ACCUM=float` (floating-point atomics)", "=", "611-618", "0.735", "-"),
             ("`DQ_SORT=0` (caller's function order instead of exponent bucket + Morton)", "=", "675", "=", "-"),
