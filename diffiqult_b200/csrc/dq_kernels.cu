@@ -806,9 +806,13 @@ __global__ void __launch_bounds__(256, PRIV ? 1 : 2) k_jk_stream(const Tile* __r
   const BlockPair b1 = s.bp[bp1];
   const bool dIJ = b1.bI == b1.bJ;
   const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, kl = lane & 15, k = kl >> 2, l = kl & 3;
-  // stages of this warp: j = warp + 8 i, tiles 2j and 2j+1 of the chunk
+  // stages of this warp: a CONTIGUOUS share j = warp * per + i of the chunk's stages (tiles 2j and 2j+1).  Consecutive tiles
+  // mostly share the ket's first block K (the kets of a bra come in K-major order, 12-24 tiles per K), so a lane's K-role
+  // sums K[I,K], K[J,K] stay in two registers while K does not change and reach the strip once per run instead of once
+  // per tile: half of the strip atomics - and the collisions of the two half-warps of a stage on them - are gone.
   const int nstage = (ch.y + 1) >> 1;
-  const int ni = nstage > warp ? (nstage - warp + 7) >> 3 : 0;
+  const int per = (nstage + 7) >> 3;
+  const int ni = max(0, min(per, nstage - warp * per));
   double* myring = ring + (size_t)warp * kJkSlots * 2 * kTile;
   unsigned long long* mybar = bars + warp * kJkSlots;
   const unsigned long long pol = l2_evict_first_policy();
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(256, PRIV ? 1 : 2) k_jk_stream(const Tile* __r
   }
   __syncwarp();
   auto issue = [&](int i) {          // lane 0: the copy of this warp's stage i into slot i % kJkSlots
-    const int j = warp + 8 * i;
+    const int j = warp * per + i;
     const unsigned bytes = (unsigned)(min(2, ch.y - 2 * j) * kTile * sizeof(double));
     unsigned long long* bar = mybar + (i % kJkSlots);
     mbar_expect_tx(bar, bytes);
@@ -850,8 +854,17 @@ __global__ void __launch_bounds__(256, PRIV ? 1 : 2) k_jk_stream(const Tile* __r
   double jacc[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) jacc[q] = 0.0;
+  double rik = 0.0, rjk = 0.0;      // K-role sums of the lane's current run: K[I_l, K_k], K[J_l, K_k]
+  int runK = -1, runnK = 0;         // first function and size of that run's K block
+  auto flush_run = [&]() {
+    if (runK >= 0 && k < runnK) {
+      if (rik != 0.0) acc_add(kstrip, l * ns + runK + k, rik, det);
+      if (rjk != 0.0) acc_add(kstrip, (4 + l) * ns + runK + k, rjk, det);
+    }
+    rik = 0.0; rjk = 0.0;
+  };
   for (int i = 0; i < ni; ++i) {
-    const int t = 2 * (warp + 8 * i) + h;
+    const int t = 2 * (warp * per + i) + h;
     const JkDesc d = desc[t < ch.y ? t : ch.y - 1];
     const bool act = t < ch.y && !d.skip;
     const bool inb = act && k < d.nK && l < d.nL;
@@ -913,16 +926,15 @@ __global__ void __launch_bounds__(256, PRIV ? 1 : 2) k_jk_stream(const Tile* __r
       if (y1 != 0.0) kp[(4 + k) * ns + cl] += y1;
       __syncwarp();
     } else if (act) {
-      if (k < d.nK) {
-        if (kik != 0.0) acc_add(kstrip, l * ns + ck, w * kik, det);
-        if (kjk != 0.0) acc_add(kstrip, (4 + l) * ns + ck, w * kjk, det);
-      }
+      if (d.sK != runK) { flush_run(); runK = d.sK; runnK = d.nK; }
+      if (k < d.nK) { rik = fma(w, kik, rik); rjk = fma(w, kjk, rjk); }
       if (l < d.nL) {
         if (kil != 0.0) acc_add(kstrip, k * ns + cl, w * kil, det);
         if (kjl != 0.0) acc_add(kstrip, (4 + k) * ns + cl, w * kjl, det);
       }
     }
   }
+  if (!PRIV) flush_run();
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
 #pragma unroll
