@@ -515,9 +515,41 @@ static void setup_jk_mode(Prepared& P, const dq_options* opt) {
   t_stats.jk_direct = P.direct ? 1 : 0;
 }
 
+// The ERI pass re-reads the primitive-pair records (15 MB for (H2O)_32) once per tile while it streams 2.6 GB of tiles out.
+// The tiles go out with evict-first stores, but how much of the record set they still push out of L2 depends on where the
+// two buffers landed physically: the pass took 230 ms in three processes of four and 260-285 ms in the fourth.  For the
+// duration of the pass the records are therefore pinned with an L2 access-policy window (persisting hits) on its stream.
+struct L2Pin {
+  cudaStream_t st; bool on = false;
+  L2Pin(cudaStream_t s, const void* base, size_t bytes) : st(s) {
+    static thread_local int limit_dev = -1;
+    int dev = 0; cudaGetDevice(&dev);
+    int maxwin = 0, maxpersist = 0;
+    cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceGetAttribute(&maxpersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (getenv("DQ_NO_L2_PIN") || maxwin <= 0 || maxpersist <= 0 || bytes == 0) return;
+    if (limit_dev != dev) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)std::min<long long>(maxpersist, 48ll << 20)); limit_dev = dev; }
+    cudaStreamAttrValue a = {};
+    a.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    a.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxwin);
+    a.accessPolicyWindow.hitRatio = 1.0f;
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    on = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess;
+    if (!on) cudaGetLastError();
+  }
+  ~L2Pin() {
+    if (!on) return;
+    cudaStreamAttrValue a = {};
+    a.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+  }
+};
+
 static void compute_eri_store(Prepared& P) {
   if (P.direct) return;
   P.d_store = P.ws.alloc<double>((size_t)P.ntiles * kTile);
+  L2Pin pin(P.ws.st, P.d_pd, (size_t)P.pd_len * sizeof(double));
   // one stream: a value tile lives ~45 us, so the tails of the class launches are negligible, and concurrent class kernels
   // made the pass time erratic (129-148 ms from run to run)
   for (int c = 15; c >= 0; --c) {        // p-rich (long) classes first

@@ -127,6 +127,8 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("row-compacted loop regime in the value kernel (reverted)", "234-249", "566", "0.74", "832-849"),
             ("private K strips per warp (`DQ_JK_PRIVATE=1`)", "-", "-", "0.96", "-"),
             ("K-run J/K kernel (no strip atomics, one CTA barrier per run; reverted)", "-", "-", "0.94", "-"),
+            ("contiguous stages per warp + K-role sums in registers (final J/K kernel)", "229.5", "565", "0.678", "826"),
+            ("pair records pinned in L2 during the ERI pass: six processes", "229.5 229.5 229.5 229.6 230.9 238.8 251.6", "565-567", "=", "826-848"),
             ("`DQ_JK_LDG=1` (register-path loads instead of the TMA ring)", "-", "-", "0.79", "-"),
             ("`DQ_ACCUM=float` (floating-point atomics)", "=", "611-618", "0.735", "-"),
             ("`DQ_SORT=0` (caller's function order instead of exponent bucket + Morton)", "=", "675", "=", "-"),
