@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in SOURCES:
         obj = os.path.join(HERE, "_lib", src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("DQ_NVCC_EXTRA", "").split()          # e.g. -DDQ_EXPERIMENT_NO_LOOPS (timing experiments)
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
     for cmd, p in procs:

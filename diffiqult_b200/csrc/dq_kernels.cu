@@ -331,6 +331,140 @@ __global__ void __launch_bounds__(256) k_eri_tiles(const Tile* __restrict__ tile
 }
 
 // ---------------------------------------------------------------------------------------------
+// ERI tiles with the LOOP-REGIME quartets deferred and compacted per tile (the default for contractions of <= 96 primitive
+// pairs per tile side product, i.e. STO-3G-like bases).  Timing experiment (DQ_EXPERIMENT_NO_LOOPS build): on the dense
+// (H2O)_32 cluster the 6 % of the primitive quartets whose Boys argument lies below the mid range cost 42 % of the pass
+// (229 ms against 134 ms when they are sent through the loop-free branch): they drag whole warps through the series /
+// continued-fraction loops with 8 of 32 lanes on.  Compaction inside a warp or a row does not pay (k_eri_tiles_b);
+// what does is taking them out of the warp's instruction stream altogether:
+//   phase A  every thread walks its 81 primitive quartets as k_eri_tiles does, evaluates the loop-free ones (closed form /
+//            mid range: no loop code is compiled into this phase) and only MARKS the others - one bit per step in a
+//            3-word mask - counting them per bin of the Boys argument (32 bins below the mid range);
+//   list     after a scan of the bin counts the marked quartets are listed bin by bin (shared-memory cursor per bin), so
+//            that the lanes of a warp of phase B run series / fraction loops of like length;
+//   phase B  the 256 threads take list entries round robin - whoever owns them - evaluate the quartet with the loop
+//            code, and add the value to the owner's accumulator in shared memory: fixed point (two 64-bit limbs), so the
+//            sum does not depend on who finishes first.  The tile value is phase A's register sum plus that accumulator:
+//            bit-reproducible, and equal to k_eri_tiles' value up to the order of the additions.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDefMaxSteps = 96;      // primitive quartets per contracted quartet the 3-word mask can mark
+
+__device__ __forceinline__ void det_add_shared(unsigned long long* p, double x) {      // dq::det_add on a shared-memory limb pair
+  const double h = rint(x * 16777216.0);
+  const double r = fma(-h, 1.0 / 16777216.0, x);
+  const long long hi = (long long)h, lo = (long long)rint(r * 147573952589676412928.0);
+  if (hi != 0) atomicAdd(p, (unsigned long long)hi);
+  if (lo != 0) atomicAdd(p + 1, (unsigned long long)lo);
+}
+
+template <bool LA, bool LB, bool LC, bool LD, bool ZS>
+__global__ void __launch_bounds__(256) k_eri_tiles_def(const Tile* __restrict__ tiles, SystemDev s, const double* __restrict__ pd,
+                                                       double* __restrict__ store) {
+  constexpr int L = (int)LA + (int)LB + (int)LC + (int)LD;
+  extern __shared__ double sm[];
+  __shared__ int s_cnt[32], s_cur[32], s_total;
+  if (tile_screened(s, tiles[blockIdx.x])) {
+    store[(long long)blockIdx.x * kTile + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) atomicAdd(s.skipped, 1ULL);
+    return;
+  }
+  const TileCtx c = tile_ctx(tiles[blockIdx.x], s);
+  const int KKb = c.b1.KK, KKk = c.b2.KK;            // KKb * KKk <= kDefMaxSteps (host)
+  const int tid = threadIdx.x;
+  double* sbra = sm;
+  double* sket = sbra + KKb * kPairFields * 16;
+  unsigned long long* accfx = (unsigned long long*)(sket + KKk * kPairFields * 16);      // [256][2]
+  unsigned short* items = (unsigned short*)(accfx + 512);                                 // [256 * steps] (owner << 7 | step)
+  stage_pairs(c, pd, sbra, sket);
+  accfx[2 * tid] = 0; accfx[2 * tid + 1] = 0;
+  if (tid < 32) s_cnt[tid] = 0;
+  __syncthreads();
+  const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+  const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+  const double tmid = boys_midrange_from<L>();
+  const double binscale = 31.99 / tmid;      // 32 bins of the Boys argument below the mid range
+  auto bin_of = [&](double t) { return t > 0.0 ? min(31, (int)(t * binscale)) : 0; };
+  // ---- phase A: loop-free quartets evaluated, loop-regime quartets marked and counted per argument bin
+  double v = 0.0;
+  unsigned m0 = 0u, m1 = 0u, m2 = 0u;      // (three scalars: a dynamically indexed array would live in local memory)
+  for (int pb = 0; pb < KKb; ++pb) {
+    const double* brec = sbra + pb * kPairFields * 16;
+    const PairPrim bra = load_pair(brec, c.bl);
+    if (!c.valid || (ZS && bra.K == 0.0)) continue;
+    double bs[4] = {0.0, 0.0, 0.0, 0.0};
+    if (LA) bs[0] = brec[ia * 16 + c.bl];
+    if (LB) bs[1] = brec[ib * 16 + c.bl];
+    if (LC) bs[2] = brec[ic * 16 + c.bl];
+    if (LD) bs[3] = brec[id * 16 + c.bl];
+    for (int pk = 0; pk < KKk; ++pk) {
+      const int st = pb * KKk + pk;
+      const double* krec = sket + pk * kPairFields * 16;
+      const PairPrim ket = load_pair(krec, c.kt);
+      if (ZS && ket.K == 0.0) continue;
+      const double t = prim_quartet_t(bra, ket);
+      if (!(t >= tmid)) {                       // (a NaN argument goes to the loops, which flag it)
+        const unsigned bit = 1u << (st & 31);
+        if (st < 32) m0 |= bit; else if (st < 64) m1 |= bit; else m2 |= bit;
+        atomicAdd(&s_cnt[bin_of(t)], 1);
+        continue;
+      }
+      double ds[4] = {0.0, 0.0, 0.0, 0.0};
+      if (LA) ds[0] = bs[0] - krec[ia * 16 + c.kt];
+      if (LB) ds[1] = bs[1] - krec[ib * 16 + c.kt];
+      if (LC) ds[2] = bs[2] - krec[ic * 16 + c.kt];
+      if (LD) ds[3] = bs[3] - krec[id * 16 + c.kt];
+      v += prim_quartet<LA, LB, LC, LD, false, kBoysNoLoops>(bra, ket, ds, dl, c_boys, 0.0, nullptr);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {                               // exclusive scan of the 32 bin counts
+    const int cnt = s_cnt[tid];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+    s_cur[tid] = incl - cnt;
+    if (tid == 31) s_total = incl;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (total > 0) {                              // CTA-uniform
+    // the marked quartets listed by argument bin: the lanes of a warp of phase B run loops of like length
+#pragma unroll
+    for (int wd = 0; wd < 3; ++wd) {
+      for (unsigned m = wd == 0 ? m0 : (wd == 1 ? m1 : m2); m; m &= m - 1) {
+        const int st = wd * 32 + __ffs(m) - 1;
+        const int pb = st / KKk, pk = st - pb * KKk;
+        const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
+        items[atomicAdd(&s_cur[bin_of(prim_quartet_t(bra, ket))], 1)] = (unsigned short)((tid << 7) | st);
+      }
+    }
+    __syncthreads();
+    // ---- phase B: list entries round robin, whoever owns them
+    for (int x = tid; x < total; x += 256) {
+      const int item = items[x];
+      const int owner = item >> 7, st = item & 127;
+      const int pb = st / KKk, pk = st - pb * KKk;
+      const int bl = owner >> 4, kt = owner & 15;
+      const double* brec = sbra + pb * kPairFields * 16;
+      const double* krec = sket + pk * kPairFields * 16;
+      const PairPrim bra = load_pair(brec, bl);
+      const PairPrim ket = load_pair(krec, kt);
+      double ds[4] = {0.0, 0.0, 0.0, 0.0};
+      if (LA) ds[0] = brec[ia * 16 + bl] - krec[ia * 16 + kt];
+      if (LB) ds[1] = brec[ib * 16 + bl] - krec[ib * 16 + kt];
+      if (LC) ds[2] = brec[ic * 16 + bl] - krec[ic * 16 + kt];
+      if (LD) ds[3] = brec[id * 16 + bl] - krec[id * 16 + kt];
+      const double r = prim_quartet<LA, LB, LC, LD, false, kBoysLoopsOnly>(bra, ket, ds, dl, c_boys, 0.0, nullptr);
+      det_add_shared(accfx + 2 * owner, r);
+    }
+    __syncthreads();
+    v += (double)(long long)accfx[2 * tid] * (1.0 / 16777216.0) + (double)(long long)accfx[2 * tid + 1] * (1.0 / 147573952589676412928.0);
+  }
+  __stcs(store + (long long)blockIdx.x * kTile + tid, v);      // streaming store, see k_eri_tiles
+}
+
+// ---------------------------------------------------------------------------------------------
 // ERI tiles with WARP-BATCHED Boys evaluation (opt-in: DQ_ERI_KERNEL=batched; measured SLOWER than the plain kernel, see
 // eri_launch - kept for A/B runs).  ncu on the dense (H2O)_32 cluster: 79 % of the primitive
 // quartets have t >= 50 (closed form), but 46 % of a warp's primitive-quartet steps contain at least one lane below it, and
@@ -2245,12 +2379,29 @@ void launch_one_electron_grad(cudaStream_t st, const SystemDev& s, int kmax, con
 
 template <bool A, bool B, bool C, bool D>
 static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store, size_t smem) {
-  // default: the plain kernel (Boys function evaluated in place).  DQ_ERI_KERNEL=batched selects the warp-batched variant
-  // for A/B runs: measured on the dense (H2O)_32 cluster it raises the lanes per instruction from 17.7 to 23.5 but executes
+  // default: k_eri_tiles_def where it applies, else the plain kernel (Boys function evaluated in place; forced with
+  // DQ_ERI_KERNEL=plain).  DQ_ERI_KERNEL=batched selects the warp-batched variant for A/B runs: measured on the dense (H2O)_32 cluster it raises the lanes per instruction from 17.7 to 23.5 but executes
   // 211 instead of 132 thread instructions per primitive quartet (arguments computed twice, task lists, values through
   // shared memory): 305 ms against 282 ms for the pass.
-  static const bool plain = !(getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'b');
+  // (read at every launch: the tests switch the variants inside one process)
+  const bool plain = !(getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'b');
+  const bool nodef = getenv("DQ_ERI_KERNEL") != nullptr && getenv("DQ_ERI_KERNEL")[0] == 'p';      // A/B: "plain" = loops in place
   constexpr int L = (int)A + (int)B + (int)C + (int)D;
+  // smem = two staged block pairs of kkmax primitive pairs each: kkmax = smem / (2 * 8 * 16 * 8)
+  const int kkmax = (int)(smem / (2 * kPairFields * 16 * sizeof(double)));
+  if (plain && !nodef && kkmax * kkmax <= kDefMaxSteps) {
+    // records + accumulators [256][2] + items [256 * steps]
+    const size_t smem_def = smem + 512 * sizeof(unsigned long long) + (size_t)256 * kkmax * kkmax * sizeof(unsigned short) + 16;
+    if (s.zero_skip) {
+      ensure_dynamic_smem(k_eri_tiles_def<A, B, C, D, true>, 200 * 1024, true);
+      k_eri_tiles_def<A, B, C, D, true><<<nt, 256, smem_def, st>>>(tiles, s, pd, store);
+    } else {
+      ensure_dynamic_smem(k_eri_tiles_def<A, B, C, D, false>, 200 * 1024, true);
+      k_eri_tiles_def<A, B, C, D, false><<<nt, 256, smem_def, st>>>(tiles, s, pd, store);
+    }
+    DQ_LAUNCHED();
+    return;
+  }
   const size_t smem_b = smem + (size_t)8 * kBoysCap * (L + 2) * sizeof(double);
   if (!plain && smem_b <= 200 * 1024) {
     if (s.zero_skip) {

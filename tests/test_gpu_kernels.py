@@ -83,6 +83,29 @@ def test_exact_zero_primitive_pairs_are_skipped_bit_identically(monkeypatch):
     assert abs(og["grad"][1]) > 1e-3 and np.abs(r["grad"][1] - og["grad"]).max() < TOL_G
 
 
+@pytest.mark.parametrize("name", ["h2o_sto3g", "ch2o", "ch4_sto3g", "hcn_sto3g", "w2", "w4"])
+def test_deferred_loop_regime_eri_kernel_equals_plain_and_oracle(monkeypatch, name):
+    """k_eri_tiles_def (the default for STO-3G-like contractions: loop-regime primitive quartets of a tile marked in phase A,
+    listed by Boys-argument bin and evaluated by whichever thread comes next in phase B, summed in fixed point) against the
+    plain kernel (DQ_ERI_KERNEL=plain: Boys loops in place) and the oracle; molecules put most quartets in the loop regime,
+    the water dimer / tetramer of the dense cluster mix all regimes.  Two calls return identical bits."""
+    if name.startswith("w"):
+        mol, basis, ne = synthetic.water_cluster(int(name[1:]), spacing=5.67), basis_set_3G_STO, 10 * int(name[1:])
+    else:
+        mol, basis, ne = (systems.SYSTEMS if name in systems.SYSTEMS else systems.EXTRA_SYSTEMS)[name]
+    s = System_mol(mol, basis, ne, name)
+    cn = Integrals.normalization(s.alpha, s.coef, s.l, s.list_contr)
+    monkeypatch.setenv("DQ_ERI_KERNEL", "plain")
+    e0 = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    monkeypatch.delenv("DQ_ERI_KERNEL")
+    e1 = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    e2 = Integrals.erivector(s.alpha, cn, s.xyz, s.l, s.nbasis, s.list_contr)
+    assert np.array_equal(e1, e2)
+    assert np.abs(e1 - e0).max() < 1e-13 * max(1.0, np.abs(e0).max())
+    if s.nbasis <= 14:
+        assert np.abs(e1 - orc.eri(orc.SysArrays(s), cn)).max() < TOL_INT
+
+
 @pytest.mark.parametrize("name", ["h2", "h2o_sto3g", "ch2o", "ch4", "h2_6g", "h4_6g", "h2o_mixed"])
 def test_compacting_eri_kernel_equals_plain_and_oracle(monkeypatch, name):
     """The ERI kernel that lists the surviving primitive pairs of a tile and walks their Cartesian product (chosen
