@@ -2389,7 +2389,10 @@ static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemD
   constexpr int L = (int)A + (int)B + (int)C + (int)D;
   // smem = two staged block pairs of kkmax primitive pairs each: kkmax = smem / (2 * 8 * 16 * 8)
   const int kkmax = (int)(smem / (2 * kPairFields * 16 * sizeof(double)));
-  if (plain && !nodef && kkmax * kkmax <= kDefMaxSteps) {
+  // (classes with fewer than two p functions have a Boys evaluation so cheap that the four CTA barriers of the deferred
+  //  form cost more than its loops: ncu per class, (ss|ss) 15.1 against 12.3 ms, (ss|sp) 37.9 against 35.2, but (sp|sp)
+  //  49.2 against 55.6, (sp|pp) 58.8 against 60.0, (pp|pp) 14.2 against 20.4)
+  if (plain && !nodef && L >= 2 && kkmax * kkmax <= kDefMaxSteps) {
     // records + accumulators [256][2] + items [256 * steps]
     const size_t smem_def = smem + 512 * sizeof(unsigned long long) + (size_t)256 * kkmax * kkmax * sizeof(unsigned short) + 16;
     if (s.zero_skip) {
