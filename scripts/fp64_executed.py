@@ -31,8 +31,10 @@ for fi, one in enumerate(src.split(",")):
         per.setdefault((fi, r[0], name), {})[r[12]] = float(r[14].replace(",", ""))
     seen_fams |= fams_here
 fam = {}
+ALIAS = {"k_eri_tiles_def": "k_eri_tiles"}      # the value pass launches k_eri_tiles (L < 2) and k_eri_tiles_def (L >= 2): one family
 for (_, _, name), m in per.items():
-    f = name.split("<")[0]
+    f = name.split("<")[0].replace("dq::", "")
+    f = ALIAS.get(f, f)
     a = fam.setdefault(f, {"launches": 0, "flop": 0.0, "inst": 0.0, "ns": 0.0, "pipe_ns": 0.0, "dram": 0.0, "winst": 0.0, "tinst": 0.0})
     wi = m.get("smsp__inst_executed.sum", 0.0)
     a["winst"] += wi

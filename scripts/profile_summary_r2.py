@@ -99,7 +99,8 @@ for e in after[:1]:
 stall_table("Gradient kernel, class (sp|pp) - the largest launch of the dominant family", ent)
 w("In between (Boys series fully unrolled in the gradient kernels, 58 KB of code): `no_instruction` 2.63, 195 ms for this launch - the "
   "instruction-cache episode of DESIGN.md 3.\n")
-stall_table("Value kernel, class (sp|pp)", [("k_eri_tiles<0,1,1,1>", raw("profiles/r2_ncu_full_eri.raw.csv")[0])])
+_v = raw("profiles/r2_ncu_full_eri.raw.csv")
+stall_table("Value kernels (the two launches captured)", [(re.sub(r"\(.*", "", e["Kernel Name"]).replace("void ", "").replace("dq::", ""), e) for e in _v if e.get("smsp__inst_executed.sum", "nan") not in ("nan", "-nan", "")][:2])
 jk = raw("profiles/r2_ncu_full_jk.raw.csv")[0]
 stall_table("J/K contraction (one Fock build)", [("k_jk_stream", jk)])
 
@@ -128,6 +129,8 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("private K strips per warp (`DQ_JK_PRIVATE=1`)", "-", "-", "0.96", "-"),
             ("K-run J/K kernel (no strip atomics, one CTA barrier per run; reverted)", "-", "-", "0.94", "-"),
             ("contiguous stages per warp + K-role sums in registers (final J/K kernel)", "229.5", "565", "0.678", "826"),
+            ("deferred value kernel, list step-major / by argument bin / by bin and only for classes with >= 2 p functions (final)", "232-242 / 219.5-226 / 213-221", "565", "0.678", "829 / 816 / 810"),
+            ("timing experiment: loop-regime quartets sent through the loop-free branch (wrong numbers)", "133.7", "324.2", "-", "-"),
             ("pair records pinned in L2 during the ERI pass: six processes", "229.5 229.5 229.5 229.6 230.9 238.8 251.6", "565-567", "=", "826-848"),
             ("`DQ_JK_LDG=1` (register-path loads instead of the TMA ring)", "-", "-", "0.79", "-"),
             ("`DQ_ACCUM=float` (floating-point atomics)", "=", "611-618", "0.735", "-"),
