@@ -387,6 +387,11 @@ __global__ void __launch_bounds__(256) k_eri_tiles_def(const Tile* __restrict__ 
   // ---- phase A: loop-free quartets evaluated, loop-regime quartets marked and counted per argument bin
   double v = 0.0;
   unsigned m0 = 0u, m1 = 0u, m2 = 0u;      // (three scalars: a dynamically indexed array would live in local memory)
+  // the argument bins of the first 36 marked quartets, 5 bits each, in marking order: listing them needs no second
+  // evaluation of t (ncu: recomputing it for every listed quartet made the listing loop 12 % of the kernel's instructions
+  // at 6 lanes per instruction)
+  unsigned long long p0 = 0ull, p1 = 0ull, p2 = 0ull;
+  int nmark = 0;
   for (int pb = 0; pb < KKb; ++pb) {
     const double* brec = sbra + pb * kPairFields * 16;
     const PairPrim bra = load_pair(brec, c.bl);
@@ -405,7 +410,12 @@ __global__ void __launch_bounds__(256) k_eri_tiles_def(const Tile* __restrict__ 
       if (!(t >= tmid)) {                       // (a NaN argument goes to the loops, which flag it)
         const unsigned bit = 1u << (st & 31);
         if (st < 32) m0 |= bit; else if (st < 64) m1 |= bit; else m2 |= bit;
-        atomicAdd(&s_cnt[bin_of(t)], 1);
+        const int bin = bin_of(t);
+        atomicAdd(&s_cnt[bin], 1);
+        if (nmark < 12) p0 |= (unsigned long long)bin << (5 * nmark);
+        else if (nmark < 24) p1 |= (unsigned long long)bin << (5 * (nmark - 12));
+        else if (nmark < 36) p2 |= (unsigned long long)bin << (5 * (nmark - 24));
+        ++nmark;
         continue;
       }
       double ds[4] = {0.0, 0.0, 0.0, 0.0};
@@ -429,14 +439,22 @@ __global__ void __launch_bounds__(256) k_eri_tiles_def(const Tile* __restrict__ 
   const int total = s_total;
   if (total > 0) {                              // CTA-uniform
     // the marked quartets listed by argument bin: the lanes of a warp of phase B run loops of like length
+    int j = 0;
 #pragma unroll
     for (int wd = 0; wd < 3; ++wd) {
-      for (unsigned m = wd == 0 ? m0 : (wd == 1 ? m1 : m2); m; m &= m - 1) {
+      for (unsigned m = wd == 0 ? m0 : (wd == 1 ? m1 : m2); m; m &= m - 1, ++j) {
         const int st = wd * 32 + __ffs(m) - 1;
-        const int pb = st / KKk, pk = st - pb * KKk;
-        const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
-        const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
-        items[atomicAdd(&s_cur[bin_of(prim_quartet_t(bra, ket))], 1)] = (unsigned short)((tid << 7) | st);
+        int bin;
+        if (j < 36) {
+          const unsigned long long pw = j < 12 ? p0 : (j < 24 ? p1 : p2);
+          bin = (int)((pw >> (5 * (j % 12))) & 31ull);
+        } else {                                 // more than 36 marked quartets in one thread: recompute
+          const int pb = st / KKk, pk = st - pb * KKk;
+          const PairPrim bra = load_pair(sbra + pb * kPairFields * 16, c.bl);
+          const PairPrim ket = load_pair(sket + pk * kPairFields * 16, c.kt);
+          bin = bin_of(prim_quartet_t(bra, ket));
+        }
+        items[atomicAdd(&s_cur[bin], 1)] = (unsigned short)((tid << 7) | st);
       }
     }
     __syncthreads();

@@ -130,6 +130,7 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("K-run J/K kernel (no strip atomics, one CTA barrier per run; reverted)", "-", "-", "0.94", "-"),
             ("contiguous stages per warp + K-role sums in registers (final J/K kernel)", "229.5", "565", "0.678", "826"),
             ("deferred value kernel, list step-major / by argument bin / by bin and only for classes with >= 2 p functions (final)", "232-242 / 219.5-226 / 213-221", "565", "0.678", "829 / 816 / 810"),
+            ("+ argument bins packed in registers at marking time (no second evaluation of t when listing): six processes", "208.2 208.2 208.2 209.2 219.0 222.1", "565-566", "=", "805-819"),
             ("timing experiment: loop-regime quartets sent through the loop-free branch (wrong numbers)", "133.7", "324.2", "-", "-"),
             ("pair records pinned in L2 during the ERI pass: six processes", "229.5 229.5 229.5 229.6 230.9 238.8 251.6", "565-567", "=", "826-848"),
             ("`DQ_JK_LDG=1` (register-path loads instead of the TMA ring)", "-", "-", "0.79", "-"),
