@@ -1305,10 +1305,11 @@ constexpr int kSparseChunk = 20;   // tiles per chunk of the sparse-weight gradi
 // (With one tile per CTA the 8 warps drifted apart over the 81 primitive quartets of a tile and ~10 % of the stall
 // samples sat on the end-of-tile barrier.)
 // ---------------------------------------------------------------------------------------------
-// occupancy: up to three p functions the kernel fits two CTAs per SM (128 registers with small spills, 2 x ~105 KB
-// shared memory); (pp|pp) needs > 200 registers and gains nothing from being squeezed (measured)
+// occupancy: two CTAs per SM for every class (128 registers, 2 x ~105 KB shared memory).  (pp|pp) wants 251 registers; with
+// the rolled Boys loops of round 2 it is faster squeezed to 128 (240 bytes of spills) at two CTAs per SM: 50 against 60 ms
+// (round 1, with the unrolled loops, measured no gain)
 template <bool LA, bool LB, bool LC, bool LD, bool ZS>
-__global__ void __launch_bounds__(256, ((int)LA + (int)LB + (int)LC + (int)LD <= 3) ? 2 : 1)
+__global__ void __launch_bounds__(256, 2)
 k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s, const double* __restrict__ pd,
                   int nterms, const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
                   double* __restrict__ pasum) {
