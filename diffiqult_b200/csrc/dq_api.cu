@@ -889,6 +889,24 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
       launch_weight_mask(st, (int)nn, nterms, Bt, d_mask);
       P.sd.wmask = d_mask;
     }
+    // deferred loop-regime quartets (dense weights, short contractions): masks of the marked primitive quartets, 3 words per
+    // thread and tile
+    unsigned* dmask = nullptr;
+    unsigned char* dbin = nullptr;
+    size_t def_off[16] = {0};
+    const char* defer_env = getenv("DQ_GRAD_DEFER");      // default on; DQ_GRAD_DEFER=0: Boys loops in place in every class
+    if (!sparse && !(defer_env && defer_env[0] == '0') && P.kkmax * P.kkmax <= 96) {
+      size_t ndef = 0;      // tiles of the classes that defer (>= 2 p functions): buffers are laid out class by class
+      for (int c = 0; c < 16; ++c) {
+        def_off[c] = ndef;
+        if (((c >> 3) & 1) + ((c >> 2) & 1) + ((c >> 1) & 1) + (c & 1) >= 2) ndef += (size_t)(P.cls_start[c + 1] - P.cls_start[c]);
+      }
+      if (ndef > 0) {
+        dmask = ws.alloc<unsigned>(ndef * 3 * 256);
+        CU(cudaMemsetAsync(dmask, 0, ndef * 3 * 256 * sizeof(unsigned), st));
+        dbin = ws.alloc<unsigned char>(ndef * 96 * 256);      // one byte per (tile, step, thread): only marked entries are written and read
+      }
+    }
     t_fork.init(ws.dev);
     t_fork.begin(st);
     for (int c = 15, lane = 0; c >= 0; --c) {
@@ -901,8 +919,15 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
       }
       const int nch = P.tp->gchunk_cls_start[c + 1] - P.tp->gchunk_cls_start[c];
       if (nch <= 0) continue;
-      launch_eri_grad_chunks(t_fork.lane(lane++), c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c], nch, P.sd, P.d_pd,
-                             nterms, At, Bt, padj, pasum, P.kkmax);
+      const int npf = ((c >> 3) & 1) + ((c >> 2) & 1) + ((c >> 1) & 1) + (c & 1);      // p functions of the class
+      unsigned* dm = (dmask && npf >= 2) ? dmask + def_off[c] * 3 * 256 : nullptr;
+      unsigned char* db = dm ? dbin + def_off[c] * 96 * 256 : nullptr;
+      cudaStream_t ls = t_fork.lane(lane++);
+      launch_eri_grad_chunks(ls, c, P.tp->d_gtiles, P.tp->d_gchunks + P.tp->gchunk_cls_start[c], nch, P.sd, P.d_pd,
+                             nterms, At, Bt, padj, pasum, P.kkmax, dm, db, P.cls_start[c]);
+      if (dm)      // the marked loop-regime quartets of this class (same stream: after its first kernel)
+        launch_eri_grad_deferred(ls, c, P.tp->d_gtiles, P.cls_start[c], P.cls_start[c + 1] - P.cls_start[c], P.sd, P.d_pd, nterms, At, Bt,
+                                 padj, pasum, dm, db, P.kkmax);
     }
     t_fork.end(st);
     t_stats.ms_eri_grad = t_gk.stop();

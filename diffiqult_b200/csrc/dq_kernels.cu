@@ -1290,6 +1290,7 @@ __global__ void k_det_finalize(long long n, const double* __restrict__ in, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kDeferWords = 3;     // deferred gradient form: 3 mask words per thread and tile (+ one bin byte per marked step in dbin)
 constexpr int kGradKetChunk = 9;   // ket primitive pairs whose adjoint slots are resident at once
 constexpr int kSparseChunk = 20;   // tiles per chunk of the sparse-weight gradient kernel (its work list lives in shared memory)
 
@@ -1308,11 +1309,16 @@ constexpr int kSparseChunk = 20;   // tiles per chunk of the sparse-weight gradi
 // occupancy: two CTAs per SM for every class (128 registers, 2 x ~105 KB shared memory).  (pp|pp) wants 251 registers; with
 // the rolled Boys loops of round 2 it is faster squeezed to 128 (240 bytes of spills) at two CTAs per SM: 50 against 60 ms
 // (round 1, with the unrolled loops, measured no gain)
-template <bool LA, bool LB, bool LC, bool LD, bool ZS>
+// DEFER (classes with >= 2 p functions, contractions of <= 96 primitive quartets): the loop-regime primitive quartets are
+// not evaluated here - no Boys loop is compiled into this kernel - but marked, one bit per (bra primitive, ket primitive)
+// step in three words per thread, and the masks go to global memory (dmask[tile][word][thread]) for k_eri_grad_deferred.
+template <bool LA, bool LB, bool LC, bool LD, bool ZS, bool DEFER>
 __global__ void __launch_bounds__(256, 2)
 k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunks, SystemDev s, const double* __restrict__ pd,
                   int nterms, const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
-                  double* __restrict__ pasum) {
+                  double* __restrict__ pasum, unsigned* __restrict__ dmask, unsigned char* __restrict__ dbin, int tile0) {
+  constexpr int L = (int)LA + (int)LB + (int)LC + (int)LD;
+  const double tmid = boys_midrange_from<L>();
   extern __shared__ double sm[];
   const int2 ch = chunks[blockIdx.x];
   const int bp2 = tiles[ch.x].bp2;
@@ -1367,6 +1373,9 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
       const long long off5b = b1.off / kPairFields * kAdjFields;
       const double* gbra = pd + b1.off * 16;
       double pas = 0.0, pbs = 0.0;
+      unsigned m0 = 0u, m1 = 0u, m2 = 0u;      // DEFER: marked steps pb * KKk + pk
+      const double binscale = 31.99 / tmid;      // ... their Boys-argument bins go straight to global memory (one byte each)
+      unsigned char* tbin = DEFER ? dbin + (long long)(ch.x + ti - tile0) * kDefMaxSteps * 256 + tid : nullptr;      // (class-relative tile index)
       for (int pb = 0; pb < KKb; ++pb) {
         const double* brec = gbra + pb * kPairFields * 16;
         PairAdj ba; ba.P[0] = ba.P[1] = ba.P[2] = ba.g = ba.K = 0.0;
@@ -1390,7 +1399,19 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
             if (LC) ds[2] = bs[2] - krec[ic * 16 + kt];
             if (LD) ds[3] = bs[3] - krec[id * 16 + kt];
             QuartetAdj q;
-            prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
+            if (DEFER) {
+              const double tq = prim_quartet_t(bra, ket);
+              if (!(tq >= tmid)) {      // loop regime: marked for the second kernel
+                const int st = pb * KKk + k0 + pk;
+                const unsigned bit = 1u << (st & 31);
+                if (st < 32) m0 |= bit; else if (st < 64) m1 |= bit; else m2 |= bit;
+                tbin[st * 256] = (unsigned char)(tq > 0.0 ? min(31, (int)(tq * binscale)) : 0);
+                continue;
+              }
+              prim_quartet<LA, LB, LC, LD, true, kBoysNoLoops>(bra, ket, ds, dl, c_boys, W, &q);
+            } else {
+              prim_quartet<LA, LB, LC, LD, true>(bra, ket, ds, dl, c_boys, W, &q);
+            }
             ba.P[0] += q.dP[0]; ba.P[1] += q.dP[1]; ba.P[2] += q.dP[2]; ba.g += q.gb; ba.K += q.Kb;
             if (LA) { bsl[0] += q.ds[0] + q.e[0]; pas += q.e[0]; }      // bra.pa = bra.P[ia] - A[ia]
             if (LB) { bsl[1] += q.ds[1] + q.e[1]; pbs += q.e[1]; }
@@ -1430,6 +1451,10 @@ k_eri_grad_chunks(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
           if (pas != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 0) * 16 + bl, pas, s.det);
           if (pbs != 0.0) acc_add(pasum, ((long long)tl.bp1 * 2 + 1) * 16 + bl, pbs, s.det);
         }
+      }
+      if (DEFER && __any_sync(0xffffffffu, (m0 | m1 | m2) != 0u)) {      // (the mask buffer is zeroed by the host)
+        unsigned* mp = dmask + ((long long)(ch.x + ti - tile0) * kDeferWords) * 256 + tid;
+        mp[0] = m0; mp[256] = m1; mp[512] = m2;
       }
     }
     const bool last = k0 + kn >= KKk;
@@ -1607,6 +1632,170 @@ k_eri_grad_sparse(const Tile* __restrict__ tiles, const int2* __restrict__ chunk
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
     if ((tid & 31) == 0 && nzero) atomicAdd(s.zero_weight, (unsigned long long)nzero);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ERI gradient, second kernel of the DEFERRED form: the loop-regime primitive quartets k_eri_grad_chunks<..., DEFER> marked.
+// One CTA per tile; CTAs of tiles without marks leave after reading their 3 KB of masks.  Otherwise, as in k_eri_tiles_def:
+// the marked quartets are counted per bin of the Boys argument, listed bin by bin, and taken round robin by the 256
+// threads - whoever owns them - with the loop code of the Boys function; what differs is the delivery: a gradient quartet
+// has 14 sums to deliver (5 + 2 adjoints of its bra primitive pair, 5 + 2 of its ket primitive pair) instead of one value.
+// They go to fixed-point accumulators in shared memory (one per primitive-pair field of the tile's two block pairs: the
+// order of the atomics does not matter), which are added limb by limb to the global accumulators at the end.
+// ---------------------------------------------------------------------------------------------
+template <bool LA, bool LB, bool LC, bool LD>
+__global__ void __launch_bounds__(256, 2)
+k_eri_grad_deferred(const Tile* __restrict__ tiles, int tile0, SystemDev s, const double* __restrict__ pd, int nterms,
+                    const double* __restrict__ At, const double* __restrict__ Bt, double* __restrict__ padj,
+                    double* __restrict__ pasum, const unsigned* __restrict__ dmask, const unsigned char* __restrict__ dbin) {
+  constexpr int L = (int)LA + (int)LB + (int)LC + (int)LD;
+  extern __shared__ double sm[];
+  __shared__ int s_cnt[32], s_cur[32], s_total, s_any;
+  const int tid = threadIdx.x;
+  const long long tix = (long long)tile0 + blockIdx.x;
+  const unsigned* mp = dmask + ((long long)blockIdx.x * kDeferWords) * 256 + tid;      // (dmask / dbin: class-relative tile index)
+  const unsigned m0 = mp[0], m1 = mp[256], m2 = mp[512];
+  if (tid == 0) s_any = 0;
+  if (tid < 32) s_cnt[tid] = 0;
+  __syncthreads();
+  if ((m0 | m1 | m2) != 0u) s_any = 1;
+  __syncthreads();
+  if (!s_any) return;
+  const Tile tl = tiles[tix];
+  const TileCtx c = tile_ctx(tl, s);
+  const int KKb = c.b1.KK, KKk = c.b2.KK;
+  const int nfb = KKb * kAdjFields + 2, nfk = KKk * kAdjFields + 2;      // accumulator fields per bra / ket lane
+  double* sbra = sm;
+  double* sket = sbra + KKb * kPairFields * 16;
+  double* sW = sket + KKk * kPairFields * 16;                             // [256] weights of the tile's quartets
+  unsigned long long* accb = (unsigned long long*)(sW + 256);             // [16][nfb][2]
+  unsigned long long* acck = accb + 16 * nfb * 2;                         // [16][nfk][2]
+  unsigned short* items = (unsigned short*)(acck + 16 * nfk * 2);         // [256 * steps]
+  stage_pairs(c, pd, sbra, sket);
+  for (int x = tid; x < 16 * (nfb + nfk) * 2; x += 256) accb[x] = 0ull;
+  // the weight of this thread's quartet, exactly as in k_eri_grad_chunks
+  {
+    const int n = s.N;
+    const size_t nn = (size_t)n * n;
+    double W = 0.0;
+    if (c.valid && (m0 | m1 | m2) != 0u) {      // only the owners of marked quartets need their weight (108 scattered loads)
+      const int i = c.b1.sI + c.il, j = c.b1.sJ + c.jl, k = c.b2.sI + c.kl, l = c.b2.sJ + c.ll;
+      for (int t = 0; t < nterms; ++t) {
+        const double* A = At + t * nn;
+        const double* B = Bt + t * nn;
+        W += 8.0 * (A[i * n + j] * B[k * n + l] + A[k * n + l] * B[i * n + j]) -
+             2.0 * (A[i * n + k] * B[j * n + l] + A[j * n + k] * B[i * n + l] + A[i * n + l] * B[j * n + k] +
+                    A[j * n + l] * B[i * n + k]);
+      }
+      W *= (tl.bp1 == tl.bp2 ? 0.5 : 1.0) * (c.b1.bI == c.b1.bJ ? 0.5 : 1.0) * (c.b2.bI == c.b2.bJ ? 0.5 : 1.0);
+    }
+    sW[tid] = W;
+  }
+  __syncthreads();
+  const int ia = c.b1.axI, ib = c.b1.axJ, ic = c.b2.axI, id = c.b2.axJ;
+  const AxisDeltas dl = quartet_deltas<LA, LB, LC, LD>(ia, ib, ic, id);
+  const double tmid = boys_midrange_from<L>();
+  const double binscale = 31.99 / tmid;
+  auto bin_of = [&](double t) { return t > 0.0 ? min(31, (int)(t * binscale)) : 0; };
+  // count the marks per argument bin; the first kernel left the bin of every marked step in dbin (one byte): listing
+  // needs no second evaluation of t (ncu: recomputing it made the two listing loops 29 % of this kernel's instructions at
+  // 6 lanes per instruction)
+  const unsigned char* tbin = dbin + (long long)blockIdx.x * kDefMaxSteps * 256 + tid;
+  auto bin_at = [&](int, int st) -> int { return tbin[st * 256] & 31; };
+  (void)bin_of; (void)tmid;
+  {
+    int j = 0;
+#pragma unroll
+    for (int wd = 0; wd < 3; ++wd) {
+      for (unsigned m = wd == 0 ? m0 : (wd == 1 ? m1 : m2); m; m &= m - 1, ++j) atomicAdd(&s_cnt[bin_at(j, wd * 32 + __ffs(m) - 1)], 1);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int cnt = s_cnt[tid];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+    s_cur[tid] = incl - cnt;
+    if (tid == 31) s_total = incl;
+  }
+  __syncthreads();
+  const int total = s_total;
+  {
+    int j = 0;
+#pragma unroll
+    for (int wd = 0; wd < 3; ++wd) {
+      for (unsigned m = wd == 0 ? m0 : (wd == 1 ? m1 : m2); m; m &= m - 1, ++j) {
+        const int st = wd * 32 + __ffs(m) - 1;
+        items[atomicAdd(&s_cur[bin_at(j, st)], 1)] = (unsigned short)((tid << 7) | st);
+      }
+    }
+  }
+  __syncthreads();
+  // the listed quartets, round robin
+  for (int x = tid; x < total; x += 256) {
+    const int item = items[x];
+    const int owner = item >> 7, st = item & 127;
+    const int pb = st / KKk, pk = st - pb * KKk;
+    const int bl = owner >> 4, kt = owner & 15;
+    const double* brec = sbra + pb * kPairFields * 16;
+    const double* krec = sket + pk * kPairFields * 16;
+    const PairPrim bra = load_pair(brec, bl);
+    const PairPrim ket = load_pair(krec, kt);
+    double ds[4] = {0.0, 0.0, 0.0, 0.0};
+    if (LA) ds[0] = brec[ia * 16 + bl] - krec[ia * 16 + kt];
+    if (LB) ds[1] = brec[ib * 16 + bl] - krec[ib * 16 + kt];
+    if (LC) ds[2] = brec[ic * 16 + bl] - krec[ic * 16 + kt];
+    if (LD) ds[3] = brec[id * 16 + bl] - krec[id * 16 + kt];
+    QuartetAdj q;
+    prim_quartet<LA, LB, LC, LD, true, kBoysLoopsOnly>(bra, ket, ds, dl, c_boys, sW[owner], &q);
+    // bra side (k_eri_grad_chunks: ba, bsl folded into ba.P along the axes, pas / pbs)
+    double bP[3] = {q.dP[0], q.dP[1], q.dP[2]}, kP[3] = {-q.dP[0], -q.dP[1], -q.dP[2]};
+    if (LA) { add3(bP, ia, q.ds[0] + q.e[0]); add3(kP, ia, -q.ds[0]); }
+    if (LB) { add3(bP, ib, q.ds[1] + q.e[1]); add3(kP, ib, -q.ds[1]); }
+    if (LC) { add3(bP, ic, q.ds[2]); add3(kP, ic, q.e[2] - q.ds[2]); }
+    if (LD) { add3(bP, id, q.ds[3]); add3(kP, id, q.e[3] - q.ds[3]); }
+    unsigned long long* ab = accb + ((size_t)bl * nfb + pb * kAdjFields) * 2;
+    if (bP[0] != 0.0) det_add_shared(ab + 0, bP[0]);
+    if (bP[1] != 0.0) det_add_shared(ab + 2, bP[1]);
+    if (bP[2] != 0.0) det_add_shared(ab + 4, bP[2]);
+    if (q.gb != 0.0) det_add_shared(ab + 6, q.gb);
+    if (q.Kb != 0.0) det_add_shared(ab + 8, q.Kb);
+    unsigned long long* as_ = accb + ((size_t)bl * nfb + KKb * kAdjFields) * 2;
+    if (LA && q.e[0] != 0.0) det_add_shared(as_ + 0, q.e[0]);
+    if (LB && q.e[1] != 0.0) det_add_shared(as_ + 2, q.e[1]);
+    unsigned long long* ak = acck + ((size_t)kt * nfk + pk * kAdjFields) * 2;
+    if (kP[0] != 0.0) det_add_shared(ak + 0, kP[0]);
+    if (kP[1] != 0.0) det_add_shared(ak + 2, kP[1]);
+    if (kP[2] != 0.0) det_add_shared(ak + 4, kP[2]);
+    if (q.gk != 0.0) det_add_shared(ak + 6, q.gk);
+    if (q.Kk != 0.0) det_add_shared(ak + 8, q.Kk);
+    unsigned long long* aks = acck + ((size_t)kt * nfk + KKk * kAdjFields) * 2;
+    if (LC && q.e[2] != 0.0) det_add_shared(aks + 0, q.e[2]);
+    if (LD && q.e[3] != 0.0) det_add_shared(aks + 2, q.e[3]);
+  }
+  __syncthreads();
+  // shared-memory limbs -> global accumulators (integer limbs as they are in fixed-point mode, a double otherwise)
+  const long long off5b = c.b1.off / kPairFields * kAdjFields, off5k = c.b2.off / kPairFields * kAdjFields;
+  for (int x = tid; x < 16 * (nfb + nfk); x += 256) {
+    const bool isb = x < 16 * nfb;
+    const int y = isb ? x : x - 16 * nfb;
+    const int nf = isb ? nfb : nfk, KK = isb ? KKb : KKk;
+    const int lane16 = y / nf, f = y - lane16 * nf;
+    const unsigned long long hi = accb[2 * x], lo = accb[2 * x + 1];
+    if ((hi | lo) == 0ull) continue;
+    double* base;
+    long long idx;
+    if (f < KK * kAdjFields) { base = padj; idx = ((isb ? off5b : off5k) + f) * 16 + lane16; }
+    else { base = pasum; idx = ((long long)(isb ? tl.bp1 : tl.bp2) * 2 + (f - KK * kAdjFields)) * 16 + lane16; }
+    if (s.det) {
+      unsigned long long* gp = (unsigned long long*)base + 2 * idx;
+      if (hi) atomicAdd(gp, hi);
+      if (lo) atomicAdd(gp + 1, lo);
+    } else {
+      atomicAdd(base + idx, (double)(long long)hi * (1.0 / 16777216.0) + (double)(long long)lo * (1.0 / 147573952589676412928.0));
+    }
   }
 }
 
@@ -2447,13 +2636,22 @@ static void eri_launch(cudaStream_t st, const Tile* tiles, int nt, const SystemD
 }
 template <bool A, bool B, bool C, bool D>
 static void grad_launch(cudaStream_t st, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s, const double* pd,
-                        int nterms, const double* At, const double* Bt, double* padj, double* pasum, size_t smem) {
-  if (s.zero_skip) {
-    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, true>, 220 * 1024, true);   // 2 CTAs x ~105 KB
-    k_eri_grad_chunks<A, B, C, D, true><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum);
+                        int nterms, const double* At, const double* Bt, double* padj, double* pasum, size_t smem, unsigned* dmask,
+                        unsigned char* dbin, int tile0) {
+  if (dmask) {
+    if (s.zero_skip) {
+      ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, true, true>, 220 * 1024, true);
+      k_eri_grad_chunks<A, B, C, D, true, true><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum, dmask, dbin, tile0);
+    } else {
+      ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, false, true>, 220 * 1024, true);
+      k_eri_grad_chunks<A, B, C, D, false, true><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum, dmask, dbin, tile0);
+    }
+  } else if (s.zero_skip) {
+    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, true, false>, 220 * 1024, true);   // 2 CTAs x ~105 KB
+    k_eri_grad_chunks<A, B, C, D, true, false><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum, nullptr, nullptr, 0);
   } else {
-    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, false>, 220 * 1024, true);
-    k_eri_grad_chunks<A, B, C, D, false><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum);
+    ensure_dynamic_smem(k_eri_grad_chunks<A, B, C, D, false, false>, 220 * 1024, true);
+    k_eri_grad_chunks<A, B, C, D, false, false><<<nchunks, 256, smem, st>>>(tiles, chunks, s, pd, nterms, At, Bt, padj, pasum, nullptr, nullptr, 0);
   }
   DQ_LAUNCHED();
 }
@@ -2506,6 +2704,26 @@ void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const i
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
 }
+template <bool A, bool B, bool C, bool D>
+static void grad_deferred_launch(cudaStream_t st, const Tile* tiles, int tile0, int nt, const SystemDev& s, const double* pd, int nterms,
+                                 const double* At, const double* Bt, double* padj, double* pasum, const unsigned* dmask,
+                                 const unsigned char* dbin, size_t smem) {
+  ensure_dynamic_smem(k_eri_grad_deferred<A, B, C, D>, smem > 100 * 1024 ? smem : 100 * 1024, true);
+  k_eri_grad_deferred<A, B, C, D><<<nt, 256, smem, st>>>(tiles, tile0, s, pd, nterms, At, Bt, padj, pasum, dmask, dbin); DQ_LAUNCHED();
+}
+// second kernel of the deferred gradient form over the tiles [tile0, tile0 + nt) of class `cls` (indices into `tiles` = the
+// ket-ordered list the first kernel walked; dmask is indexed the same way)
+void launch_eri_grad_deferred(cudaStream_t st, int cls, const Tile* tiles, int tile0, int nt, const SystemDev& s, const double* pd,
+                              int nterms, const double* At, const double* Bt, double* padj, double* pasum, const unsigned* dmask,
+                              const unsigned char* dbin, int kkmax) {
+  if (nt <= 0) return;
+  const size_t smem = ((size_t)2 * kkmax * kPairFields * 16 + 256) * sizeof(double) +
+                      (size_t)2 * 16 * (kkmax * kAdjFields + 2) * 2 * sizeof(unsigned long long) +
+                      (size_t)256 * kkmax * kkmax * sizeof(unsigned short) + 16;
+#define CALL(a, b, c, d) grad_deferred_launch<a, b, c, d>(st, tiles, tile0, nt, s, pd, nterms, At, Bt, padj, pasum, dmask, dbin, smem)
+  DQ_CLASS_SWITCH(cls, CALL)
+#undef CALL
+}
 void launch_weight_mask(cudaStream_t st, int n2, int nterms, const double* Bt, unsigned char* mask) {
   k_weight_mask<<<cdiv(n2, 256), 256, 0, st>>>(n2, nterms, Bt, mask); DQ_LAUNCHED();
 }
@@ -2514,10 +2732,11 @@ void launch_count_nonzero(cudaStream_t st, int n2, const double* A, int* out) {
   k_count_nonzero<<<cdiv(n2, 256), 256, 0, st>>>(n2, A, out); DQ_LAUNCHED();
 }
 void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
-                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax) {
+                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax,
+                            unsigned* dmask, unsigned char* dbin, int tile0) {
   if (nchunks <= 0) return;
   const size_t smem = eri_grad_smem_bytes(kkmax);
-#define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, nterms, At, Bt, padj, pasum, smem)
+#define CALL(a, b, c, d) grad_launch<a, b, c, d>(st, tiles, chunks, nchunks, s, pd, nterms, At, Bt, padj, pasum, smem, dmask, dbin, tile0)
   DQ_CLASS_SWITCH(cls, CALL)
 #undef CALL
 }

@@ -46,7 +46,11 @@ void launch_eri_tiles(cudaStream_t st, int cls, const Tile* tiles, int nt, const
 void launch_eri_tiles_compact(cudaStream_t st, int cls, const Tile* tiles, int nt, const SystemDev& s, const double* pd, double* store,
                               int kkmax);
 void launch_eri_grad_chunks(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
-                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);
+                            const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax,
+                            unsigned* dmask = nullptr, unsigned char* dbin = nullptr, int tile0 = 0);
+void launch_eri_grad_deferred(cudaStream_t st, int cls, const Tile* tiles, int tile0, int nt, const SystemDev& s, const double* pd,
+                              int nterms, const double* At, const double* Bt, double* padj, double* pasum, const unsigned* dmask,
+                              const unsigned char* dbin, int kkmax);
 // sparse-weight variant (chunks of <= 32 tiles) and the nonzero count the host chooses by
 void launch_eri_grad_sparse(cudaStream_t st, int cls, const Tile* tiles, const int2* chunks, int nchunks, const SystemDev& s,
                             const double* pd, int nterms, const double* At, const double* Bt, double* padj, double* pasum, int kkmax);

@@ -106,6 +106,34 @@ def test_deferred_loop_regime_eri_kernel_equals_plain_and_oracle(monkeypatch, na
         assert np.abs(e1 - orc.eri(orc.SysArrays(s), cn)).max() < TOL_INT
 
 
+@pytest.mark.parametrize("name", ["h2o_sto3g", "ch2o", "hcn_sto3g", "w2", "w4"])
+def test_deferred_loop_regime_gradient_kernels_equal_in_place_form(monkeypatch, name):
+    """The gradient pass in two kernels (default for STO-3G-like contractions and classes with >= 2 p functions:
+    k_eri_grad_chunks<DEFER> marks the loop-regime primitive quartets, k_eri_grad_deferred evaluates them per tile, listed by
+    Boys-argument bin, and delivers their 14 adjoint sums through fixed-point shared-memory accumulators) against the
+    one-kernel form with the Boys loops in place (DQ_GRAD_DEFER=0): energy and all three gradient groups; where the oracle is
+    cheap, against it as well."""
+    if name.startswith("w"):
+        mol, basis, ne = synthetic.water_cluster(int(name[1:]), spacing=5.67), basis_set_3G_STO, 10 * int(name[1:])
+    else:
+        mol, basis, ne = (systems.SYSTEMS if name in systems.SYSTEMS else systems.EXTRA_SYSTEMS)[name]
+    s = System_mol(mol, basis, ne, name)
+    args = (np.log(s.alpha), s.coef, s.xyz, s.l, s.charges, s.atom, s.list_contr, s.ne)
+    monkeypatch.setenv("DQ_GRAD_DEFER", "0")
+    r0 = Energy.rhf_grad(*args, max_scf=200)
+    monkeypatch.delenv("DQ_GRAD_DEFER")
+    r1 = Energy.rhf_grad(*args, max_scf=200)
+    assert r0["status"] == r1["status"] == 0 and r0["niter"] == r1["niter"] and r0["E"] == r1["E"]
+    for n in (0, 1, 2):
+        scale = max(1.0, np.abs(r0["grad"][n]).max())
+        assert np.abs(r1["grad"][n] - r0["grad"][n]).max() < 1e-12 * scale, n
+    if name in ("h2o_sto3g", "ch2o"):
+        a = orc.SysArrays(s)
+        for n in (0, 1, 2):
+            og = orc.rhf_grad(a, n, max_scf=200)
+            assert og["status"] == 0 and np.abs(og["grad"] - np.ravel(r1["grad"][n])).max() < TOL_G, n
+
+
 @pytest.mark.parametrize("name", ["h2", "h2o_sto3g", "ch2o", "ch4", "h2_6g", "h4_6g", "h2o_mixed"])
 def test_compacting_eri_kernel_equals_plain_and_oracle(monkeypatch, name):
     """The ERI kernel that lists the surviving primitive pairs of a tile and walks their Cartesian product (chosen
