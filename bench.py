@@ -419,7 +419,7 @@ def run_ours(args):
         ms_jk_build = float(np.mean([x["ms_jk"] for x in stats])) / builds
         npq = st["n_prim_quartets"]                      # primitive quartets this rank evaluates per ERI pass
         ex = executed_counts(args.spacing) if (args.waters == 32 and args.screen <= 0) else None
-        gk = "k_eri_grad_sparse" if st["grad_kernel_sparse"] else "k_eri_grad_chunks"
+        gk = "k_eri_grad_sparse" if st["grad_kernel_sparse"] else "k_eri_grad_chunks"      # (incl. k_eri_grad_deferred, the second kernel of the L >= 2 classes)
         vk = "k_eri_tiles_compact" if st["eri_kernel_compact"] else "k_eri_tiles"      # (incl. k_eri_tiles_def, the L >= 2 classes)
         if st["jk_direct"]:
             vk = "k_jk_direct"

@@ -31,7 +31,8 @@ for fi, one in enumerate(src.split(",")):
         per.setdefault((fi, r[0], name), {})[r[12]] = float(r[14].replace(",", ""))
     seen_fams |= fams_here
 fam = {}
-ALIAS = {"k_eri_tiles_def": "k_eri_tiles"}      # the value pass launches k_eri_tiles (L < 2) and k_eri_tiles_def (L >= 2): one family
+ALIAS = {"k_eri_tiles_def": "k_eri_tiles", "k_eri_grad_deferred": "k_eri_grad_chunks"}      # value pass: k_eri_tiles (L < 2) + k_eri_tiles_def; gradient pass: k_eri_grad_chunks + k_eri_grad_deferred
+_UNUSED = {}      # the value pass launches k_eri_tiles (L < 2) and k_eri_tiles_def (L >= 2): one family
 for (_, _, name), m in per.items():
     f = name.split("<")[0].replace("dq::", "")
     f = ALIAS.get(f, f)

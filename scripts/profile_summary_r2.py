@@ -96,7 +96,9 @@ for e in before[:1]:
     ent.append(("BEFORE (round start): " + re.sub(r"\(.*", "", e["Kernel Name"]).replace("void ", ""), e))
 for e in after[:1]:
     ent.append(("AFTER: " + re.sub(r"\(.*", "", e["Kernel Name"]).replace("void ", ""), e))
-stall_table("Gradient kernel, class (sp|pp) - the largest launch of the dominant family", ent)
+stall_table("Gradient kernel, class (sp|pp) - the largest launch of the dominant family (AFTER = the first kernel of the deferred form)", ent)
+_g = raw("profiles/r2_ncu_full_gdef.raw.csv")
+stall_table("Second kernel of the deferred gradient form (loop-regime quartets, one launch)", [(re.sub(r"\(.*", "", e["Kernel Name"]).replace("void ", "").replace("dq::", ""), e) for e in _g][:1])
 w("In between (Boys series fully unrolled in the gradient kernels, 58 KB of code): `no_instruction` 2.63, 195 ms for this launch - the "
   "instruction-cache episode of DESIGN.md 3.\n")
 _v = raw("profiles/r2_ncu_full_eri.raw.csv")
@@ -131,6 +133,9 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("contiguous stages per warp + K-role sums in registers (final J/K kernel)", "229.5", "565", "0.678", "826"),
             ("deferred value kernel, list step-major / by argument bin / by bin and only for classes with >= 2 p functions (final)", "232-242 / 219.5-226 / 213-221", "565", "0.678", "829 / 816 / 810"),
             ("+ argument bins packed in registers at marking time (no second evaluation of t when listing): six processes", "208.2 208.2 208.2 209.2 219.0 222.1", "565-566", "=", "805-819"),
+            ("(pp|pp) gradient class at two CTAs per SM (128 registers)", "208", "556", "=", "796"),
+            ("gradient pass in two kernels for classes with >= 2 p functions (k_eri_grad_chunks<DEFER> + k_eri_grad_deferred): bins recomputed / packed in registers of the first kernel / one byte per marked step in global memory (final)", "208", "529 / 537 / 516", "=", "769 / 776 / 755"),
+            ("... also for the classes with one p function", "=", "518", "=", "-"),
             ("timing experiment: loop-regime quartets sent through the loop-free branch (wrong numbers)", "133.7", "324.2", "-", "-"),
             ("pair records pinned in L2 during the ERI pass: six processes", "229.5 229.5 229.5 229.6 230.9 238.8 251.6", "565-567", "=", "826-848"),
             ("`DQ_JK_LDG=1` (register-path loads instead of the TMA ring)", "-", "-", "0.79", "-"),
