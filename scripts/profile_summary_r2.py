@@ -143,8 +143,8 @@ for row in [("round start (round-1 kernels, warp-batched Boys default)", "305", 
             ("`DQ_SORT=0` (caller's function order instead of exponent bucket + Morton)", "=", "675", "=", "-"),
             ("`DQ_GRAD_CHUNK` = 6 / 12 (default) / 24 / 48 / 96", "=", "617 / 620 / 627 / 637 / 659 (before the rolled loops)", "=", "-")]:
     w("| " + " | ".join(row) + " |")
-w("\nMulti-GPU (torchrun, NCCL, final code): N=2 414 ms per step (ERI 105, gradient 281, SCF 17.0, reverse 4.5); N=4 225 ms (53.9 / 143 / 17.2 / 3.5); "
-  "N=8 125 ms (26.8 / 72.4 / 15.6 / 3.2; J/K 0.19 ms per build).  Earlier in the round (before the deferred value kernel, the J/K change and the "
-  "(pp|pp) occupancy change): N=2 462 ms, N=8 128 ms.\n")
+w("\nMulti-GPU (torchrun, NCCL, final code): N=2 397 ms per step (ERI 109, gradient 259, SCF 17.1, reverse 4.4); "
+  "N=8 121 ms (30.3 / 64.9 / 15.5 / 3.2; J/K 0.19 ms per build).  One code state earlier (gradient pass in one kernel): N=2 414, N=4 225, N=8 125 ms; "
+  "at the start of the round's GPU work: N=2 462 ms, N=8 128 ms.\n")
 open("profiles/r2_summary.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:6000])
