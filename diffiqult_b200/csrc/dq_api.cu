@@ -901,6 +901,9 @@ static void run_rhf(const dq_system* s, const dq_options* opt, ScfOut& out, bool
         def_off[c] = ndef;
         if (((c >> 3) & 1) + ((c >> 2) & 1) + ((c >> 1) & 1) + (c & 1) >= 2) ndef += (size_t)(P.cls_start[c + 1] - P.cls_start[c]);
       }
+      // 27 KB per deferring tile: fine for (H2O)_32 (17 GB of 180), not for much larger clusters - then the loops stay in place
+      size_t free_b = 0, total_b = 0;
+      if (ndef > 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && ndef * (size_t)(96 + 12) * 256 > free_b / 3) ndef = 0;
       if (ndef > 0) {
         dmask = ws.alloc<unsigned>(ndef * 3 * 256);
         CU(cudaMemsetAsync(dmask, 0, ndef * 3 * 256 * sizeof(unsigned), st));
